@@ -1,0 +1,323 @@
+#!/usr/bin/env python3
+"""bench.py — integrateCloud frames/s @ 640x480 into 2048^3 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of FRAMES_PER_STEP synthetic 640x480 depth
+frames (ICL-NUIM-shaped interior stream S2, colour on, 2048^3 / 10 m grid: BASELINE.json
+configs[2]).  The JSON line carries
+  value        frames/s with the clouds already resident in HBM (b200tsdf_integrate_device),
+  e2e          frames/s through the public API from pinned HOST buffers (H2D inside the timed
+               region, a D2H read of the per-step result),
+  roofline     achieved algorithmic GB/s of the dominant kernel against the measured HBM peak,
+  cpu_baseline the reference's CPU path timed on this box's host cores (bounded sample).
+`--impl reference` times the CPU arm alone (oracle/_ref = the reference's own sources when they
+compiled here, else the oracle port).  Under torchrun (N > 1) the volume is sharded by coarse
+cell across ranks (strong scaling: every rank sees every frame and fuses its own cells).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cpu_tsdf_b200 import synth  # noqa: E402
+
+FRAMES_PER_STEP = 32
+N_DISTINCT = 64            # distinct frames/poses cycled through (inputs 64 x 9.8 MB = 629 MB > 126 MB L2)
+RES, SIZE = 2048, 10.0
+CAM = synth.Camera()
+SCENE = synth.S2
+W, H = CAM.width, CAM.height
+
+
+def make_inputs(n=N_DISTINCT, color=True):
+    poses, clouds = [], []
+    for f in range(n):
+        pose = synth.orbit_pose(SCENE, f * (100 // n if n <= 100 else 1), 100)
+        poses.append(pose)
+        clouds.append(synth.make_frame(SCENE, pose, CAM, color=color, noise_seed=12345, frame=f))
+    return poses, clouds
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.rows, self.proc, self.gpu = [], None, gpu
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_volume(kind):
+    from oracle.oracle_py import OracleVolume
+    return OracleVolume(kind=kind, xres=RES, yres=RES, zres=RES, xsize=SIZE, ysize=SIZE, zsize=SIZE,
+                        cx=CAM.cx, cy=CAM.cy, integrate_color=1)
+
+
+def cpu_arm(poses, clouds, nframes, threads_list, kind=None):
+    """Time the reference's CPU integrateCloud on the host cores: warm the volume with a few frames,
+    then time `nframes` frames (integrateCloud only).  Best thread count wins."""
+    from oracle import oracle_py
+    if kind is None:
+        kind = "reference" if os.path.exists(oracle_py.REF_LIB) else "port"
+    best = None
+    for nt in threads_list:
+        os.environ["OMP_NUM_THREADS"] = str(nt)
+        v = oracle_volume(kind)
+        v.cfg.num_threads = nt
+        v.lib.orc_destroy(v.h)
+        import ctypes
+        v.h = v.lib.orc_create(ctypes.byref(v.cfg))
+        v.reset()
+        for i in range(2):
+            v.integrate(clouds[i % len(clouds)], poses[i % len(poses)])
+        t0 = time.perf_counter()
+        for i in range(2, 2 + nframes):
+            v.integrate(clouds[i % len(clouds)], poses[i % len(poses)])
+        dt = time.perf_counter() - t0
+        fps = nframes / dt
+        if best is None or fps > best["value"]:
+            best = {"value": fps, "cores": nt}
+    best.update({"unit": "frames/s", "kind": "reference" if kind == "reference" else "port",
+                 "sample": f"{nframes} frames of the same 640x480 S2 stream into 2048^3/10 m, colour on, after 2 warm-up frames; best of threads {threads_list}"})
+    return best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    poses, clouds = make_inputs(16)
+    nproc = os.cpu_count() or 1
+    frames_per_step = 4
+    from oracle import oracle_py
+    kind = "reference" if os.path.exists(oracle_py.REF_LIB) else "port"
+    nt = int(os.environ.get("B200TSDF_REF_THREADS", "0")) or min(nproc, 4)     # 4 threads was the reference's best
+    os.environ["OMP_NUM_THREADS"] = str(nt)
+    v = oracle_volume(kind)
+    import ctypes
+    v.cfg.num_threads = nt
+    v.lib.orc_destroy(v.h); v.h = v.lib.orc_create(ctypes.byref(v.cfg))
+    v.reset()
+    k = 0
+    for _ in range(args.warmup):
+        for _ in range(frames_per_step):
+            v.integrate(clouds[k % 16], poses[k % 16]); k += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(frames_per_step):
+            v.integrate(clouds[k % 16], poses[k % 16]); k += 1
+    dt = time.perf_counter() - t0
+    fps = args.steps * frames_per_step / dt
+    line = {
+        "impl": "reference", "metric": "integrateCloud frames/s @ 640x480 into 2048^3", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(frames_per_step, args.gpus),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nt, "kind": kind,
+                         "sample": f"{frames_per_step} frames per step of the 640x480 S2 stream into 2048^3/10 m, colour on"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(frames_per_step, n_gpus):
+    return {"workload": "ICL-NUIM-shaped synthetic 640x480 stream (scene S2: 4 m room seen from inside, sigma(z) depth noise), "
+                        "2048^3 voxels over 10 m, colour on (BASELINE.json configs[2] integrate leg)",
+            "frames_per_step": frames_per_step, "image": [W, H], "grid": RES, "grid_size_m": SIZE,
+            "point_bytes": 32, "distinct_frames": N_DISTINCT,
+            "l2": "inputs larger than L2 (64 distinct frames = 629 MB device-resident, orbit covers a >126 MB brick working set)",
+            "parallelism": "1 GPU" if n_gpus == 1 else f"volume sharded by coarse cell over {n_gpus} GPUs, every rank integrates every frame"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import cpu_tsdf_b200 as pkg
+    from cpu_tsdf_b200.build import build_library
+    build_library()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    poses, clouds = make_inputs()
+    vol = pkg.TSDFVolumeOctree(device=local_rank, pool_log2=20, shard_rank=rank, shard_count=world)
+    vol.setGridSize(SIZE, SIZE, SIZE)
+    vol.setResolution(RES, RES, RES)
+    vol.setCameraIntrinsics(CAM.fx, CAM.fy, CAM.cx, CAM.cy)
+    vol.setIntegrateColor(True)
+    vol.reset()
+
+    # device-resident inputs (torch owns the memory; the engine reads it through the C ABI)
+    d_clouds = [torch.from_numpy(c).cuda() for c in clouds]
+    # pinned host inputs for the end-to-end leg
+    h_clouds = [torch.from_numpy(c).pin_memory() for c in clouds]
+    torch.cuda.synchronize()
+    stride = 32
+
+    def step_device(k0):
+        for j in range(FRAMES_PER_STEP):
+            i = (k0 + j) % N_DISTINCT
+            vol.integrateCloudDevice(d_clouds[i].data_ptr(), H, W, stride, poses[i], rgba_off=16)
+
+    def step_host(k0):
+        for j in range(FRAMES_PER_STEP):
+            i = (k0 + j) % N_DISTINCT
+            h = h_clouds[i]
+            vol._check(vol._lib.b200tsdf_integrate(vol._h, h.data_ptr(), stride, 0, 16, W, H, pkg._ptr(poses[i])))
+        return vol.stats().n_updates         # D2H read of the step's result
+
+    # ---- device-resident leg ---------------------------------------------------------------
+    k = 0
+    for _ in range(args.warmup):
+        step_device(k); k += FRAMES_PER_STEP
+    vol.sync()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    vol.profile_begin()
+    for _ in range(args.steps):
+        step_device(k); k += FRAMES_PER_STEP
+    prof = vol.profile_end()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([prof.ms_elapsed], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    nframes = args.steps * FRAMES_PER_STEP
+    value = nframes / (ms_total / 1e3)
+
+    # ---- end-to-end leg (host buffers, public API) ---------------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_host(k); k += FRAMES_PER_STEP
+    barrier()
+    vol.profile_begin()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host(k); k += FRAMES_PER_STEP
+    prof_e = vol.profile_end()
+    wall = time.perf_counter() - t0
+    barrier()
+    e2e_ms = torch.tensor([max(prof_e.ms_elapsed, wall * 1e3)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = nframes / (float(e2e_ms.item()) / 1e3)
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    upd = torch.tensor([prof.n_updates], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(upd, op=dist.ReduceOp.SUM)
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per frame: 4 W H (depth) + N_upd * (8 read + 8 write) [+ (4+4) with colour]
+    b_alg_local = 4.0 * W * H * prof.n_frames + prof.n_updates * (16.0 + 8.0)
+    achieved = b_alg_local / (prof.ms_kernel / 1e3) / 1e9 if prof.ms_kernel > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "brick update (k_update_*)",
+                "bytes_per_launch": b_alg_local / max(1, prof.kernel_launches),
+                "us_per_launch": 1e3 * prof.ms_kernel / max(1, prof.kernel_launches),
+                "updates_per_frame": prof.n_updates / max(1, prof.n_frames)}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            nproc = os.cpu_count() or 1
+            tl = sorted({1, min(4, nproc), nproc})
+            cpu = cpu_arm(poses, clouds, 12, tl)
+        line = {
+            "metric": "integrateCloud frames/s @ 640x480 into 2048^3", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(FRAMES_PER_STEP, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s",
+                    "h2d_bytes_per_step": int(prof_e.h2d_bytes // args.steps), "d2h_bytes_per_step": int(prof_e.d2h_bytes // args.steps),
+                    "timing": "max(CUDA events on the engine stream, host wall clock) over ranks"},
+            "gpu_launches": int(prof.total_launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "updates_total": float(upd.item()),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/* b200tsdf.h — C ABI of the B200-native TSDF fusion engine (libb200tsdf.so).
+ *
+ * Drop-in boundary for the volumetric path of sdmiller/cpu_tsdf.  The reference has no FFI
+ * layer: its boundary is the C++ class surface cpu_tsdf::TSDFVolumeOctree /
+ * cpu_tsdf::MarchingCubesTSDFOctree.  Each entry point below names the reference method it
+ * replaces (paths relative to the reference tree); the C++ shim in
+ * include/cpu_tsdf_b200/tsdf_volume_octree.h and the Python mirror in cpu_tsdf_b200/ marshal
+ * PCL/Eigen-shaped arguments into these calls.  See INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative B200TSDF_E* code (the library never throws across the ABI);
+ * b200tsdf_last_error() gives a message.  A handle owns one CUDA device + one stream and is
+ * not thread-safe for concurrent mutation (same contract as the reference).
+ * There is NO CPU fallback: without a CUDA device b200tsdf_create fails with
+ * B200TSDF_ENODEVICE.
+ */
+#ifndef B200TSDF_H
+#define B200TSDF_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TSDF_OK          0
+#define B200TSDF_EINVAL     -1   /* bad argument / unsupported configuration          */
+#define B200TSDF_ENODEVICE  -2   /* no CUDA device (there is no CPU path)             */
+#define B200TSDF_ECUDA      -3   /* CUDA runtime error                                */
+#define B200TSDF_ENOMEM     -4   /* brick pool / device memory exhausted              */
+#define B200TSDF_ESTATE     -5   /* call order (e.g. integrate before reset)          */
+#define B200TSDF_EIO        -6   /* file I/O                                          */
+
+typedef struct b200tsdf b200tsdf_t;
+
+/* Mirrors the TSDFVolumeOctree setters; defaults = its constructor
+ * (src/lib/tsdf_volume_octree.cpp:54-85).  As in the reference, changes take effect at the
+ * next b200tsdf_reset() (cpp:201-211). */
+typedef struct b200tsdf_config
+{
+  int32_t xres, yres, zres;                 /* setResolution            cpp:93   */
+  float   xsize, ysize, zsize;              /* setGridSize              cpp:111  */
+  float   max_dist_pos, max_dist_neg;       /* setDepthTruncationLimits cpp:145  */
+  float   max_weight;                       /* setWeightTruncationLimit cpp:162  */
+  float   min_sensor_dist, max_sensor_dist; /* setSensorDistanceBounds  tsdf_volume_octree.h:174 */
+  float   max_cell_x, max_cell_y, max_cell_z; /* setMaxVoxelSize        tsdf_volume_octree.h:154 */
+  double  fx, fy, cx, cy;                   /* setCameraIntrinsics      cpp:176  */
+  int32_t image_width, image_height;        /* setImageSize             cpp:129  */
+  int32_t integrate_color;                  /* setIntegrateColor        tsdf_volume_octree.h:162 (colour mode "RGB") */
+  int32_t track_variance;                   /* keep OctreeNode::M_/nsample_ (octree.cpp:160-161) for .vol fidelity */
+  int32_t device;                           /* CUDA device ordinal                                */
+  int32_t pool_log2;                        /* brick pool capacity = 2^pool_log2 (0 = default 20) */
+  int32_t shard_rank, shard_count;          /* this handle owns coarse cells with hash(cell) % shard_count == shard_rank */
+  int32_t reserved[4];
+  double  global_transform[16];             /* setGlobalTransform tsdf_volume_octree.h:119; row-major 4x4 */
+} b200tsdf_config;
+
+void b200tsdf_default_config (b200tsdf_config* cfg);
+
+/* TSDFVolumeOctree ctor / dtor (cpp:54, :86) */
+int  b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out);
+void b200tsdf_destroy (b200tsdf_t* h);
+const char* b200tsdf_last_error (const b200tsdf_t* h);
+
+/* the setters: stores the configuration used by the next reset() */
+int  b200tsdf_set_config (b200tsdf_t* h, const b200tsdf_config* cfg);
+int  b200tsdf_get_config (const b200tsdf_t* h, b200tsdf_config* cfg);
+
+/* TSDFVolumeOctree::reset (cpp:201-219) */
+int  b200tsdf_reset (b200tsdf_t* h);
+
+/* TSDFVolumeOctree::integrateCloud<PointT,NormalT> (include/cpu_tsdf/impl/
+ * tsdf_volume_octree.hpp:48-103).  points: organized W x H cloud in the sensor frame,
+ * row-major (cloud(u,v) = points[v*W+u]), `stride` bytes per point, xyz as 3 floats at
+ * xyz_off, PCL colour bytes (b,g,r,a) at rgba_off or -1.  NaN z = invalid.  pose_c2w =
+ * camera->world Affine3d as a row-major 4x4.  The normals argument of the reference is unused
+ * there (hpp:51) and has no counterpart.  The host buffer is not retained after return. */
+int  b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
+                         int width, int height, const double* pose_c2w);
+/* same, with the cloud already resident in device memory of h's device (no copy, async on the
+ * handle's stream; call b200tsdf_sync before reading results on the host) */
+int  b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t stride, int xyz_off, int rgba_off,
+                                int width, int height, const double* pose_c2w);
+int  b200tsdf_sync (b200tsdf_t* h);
+
+/* getFxn / getGradient / getHessian (cpp:655-725) with mode 0, or the combined
+ * getFxnAndGradient / getFxnGradientAndHessian (cpp:728-794) with mode 1.  what: bit0 value,
+ * bit1 gradient (3 floats), bit2 hessian (9 floats, row-major).  ok[i] = the reference's bool.
+ * xyz/val/grad/hess/ok are host pointers. */
+int  b200tsdf_query (b200tsdf_t* h, const float* xyz, int n, int what, int mode,
+                     float* val, float* grad, float* hess, uint8_t* ok);
+
+/* renderView (cpp:278-424) and, with rgb_out != NULL, renderColoredView (cpp:427-450).
+ * out: (W/ds)*(H/ds) points of `stride` bytes; xyz at xyz_off, normal at normal_off
+ * (pcl::PointNormal: 0 / 16 / 48).  Camera frame, NaN xyz = miss. */
+int  b200tsdf_render (b200tsdf_t* h, const double* pose_c2w, int downsample, void* out, size_t stride,
+                      int xyz_off, int normal_off, uint8_t* rgb_out);
+
+/* MarchingCubesTSDFOctree::performReconstruction (src/lib/marching_cubes_tsdf_octree.cpp:
+ * 108-143): triangle soup, 3 vertices per triangle, global transform applied.
+ * color_mode 0 none / 1 setColorByRGB / 2 setColorByConfidence.  *verts (3 floats per vertex)
+ * and *rgb (3 bytes per vertex, or NULL) are library-owned until the next mesh call or
+ * b200tsdf_free. */
+int  b200tsdf_mesh (b200tsdf_t* h, float w_min, int color_mode, float** verts, uint8_t** rgb, size_t* nverts);
+void b200tsdf_free (void* p);
+
+/* TSDFVolumeOctree::save (cpp:222-245): reference-compatible .vol */
+int  b200tsdf_save (b200tsdf_t* h, const char* path);
+
+/* getVoxelCenter / getVoxelIndex (cpp:553-574) */
+int  b200tsdf_voxel_center (const b200tsdf_t* h, int64_t x, int64_t y, int64_t z, float* out3);
+int  b200tsdf_voxel_index (const b200tsdf_t* h, float x, float y, float z, int32_t* out3, int32_t* inside);
+
+/* ---- introspection (tests, bench accounting) ------------------------------------------- */
+typedef struct b200tsdf_stats
+{
+  int64_t n_updates;        /* voxels whose stored {sdf,weight} changed in the last frame (= addObservation calls) */
+  int64_t n_node_visits;    /* updateVoxel visits in the last frame */
+  int64_t n_culled_cells;   /* coarse cells kept by the frustum cull in the last frame */
+  int64_t n_bricks;         /* allocated bricks */
+  int64_t n_block_visits;   /* finest-tier bricks processed in the last frame */
+  int64_t pool_capacity;
+  int32_t coarse_level, finest_level, tiers, reserved;
+  double  ms_last_integrate;   /* device time of the last integrate (CUDA events on the handle's stream) */
+  double  ms_last_kernel;      /* device time of the dominant (brick update) kernel in the last integrate */
+} b200tsdf_stats;
+int  b200tsdf_get_stats (b200tsdf_t* h, b200tsdf_stats* s);
+
+/* Measurement hooks for bench.py: CUDA events on the handle's own stream (torch.cuda.Event only
+ * sees torch's stream).  profile_begin records the start event and clears the accumulators;
+ * profile_end records the end event, synchronizes and reports. */
+typedef struct b200tsdf_profile
+{
+  double  ms_elapsed;        /* start event -> end event on the handle's stream                     */
+  double  ms_kernel;         /* sum of the dominant (brick update) kernel's launch durations          */
+  int64_t kernel_launches;   /* launches of the dominant kernel                                       */
+  int64_t total_launches;    /* all kernel launches of this library in the region                     */
+  int64_t n_frames;          /* integrate calls in the region                                         */
+  int64_t n_updates;         /* sum over frames of voxels whose {sdf,weight} changed                  */
+  int64_t n_node_visits;
+  int64_t h2d_bytes, d2h_bytes; /* bytes this library copied across PCIe in the region                */
+} b200tsdf_profile;
+int  b200tsdf_profile_begin (b200tsdf_t* h);
+int  b200tsdf_profile_end (b200tsdf_t* h, b200tsdf_profile* out);
+
+/* Every existing octree node at depth >= coarse level, sorted by (level,x,y,z) — the same
+ * record the oracle dumps.  Pass all-NULL to get the count.  keys: 4 int32; dw: 2 floats;
+ * flags bit0 = has children; rgb 3 bytes; M float; ns int32. */
+int64_t b200tsdf_download_nodes (b200tsdf_t* h, int32_t* keys, float* dw, uint8_t* flags,
+                                 uint8_t* rgb, float* M, int32_t* ns);
+/* frustum-culled coarse-cell mask of getFrustumCulledVoxels (cpp:619-652): 8^coarse bytes */
+int  b200tsdf_frustum_cull (b200tsdf_t* h, const double* pose_c2w, uint8_t* mask, int32_t* kept);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,250 @@
+// tests/emu/emu.cpp — HOST EMULATION of the engine's device code.  TEST HARNESS ONLY.
+//
+// There is no GPU in the development container, so this file compiles the engine's
+// __host__ __device__ core (cpu_tsdf_b200/csrc/tsdf_core.cuh — the very code the CUDA kernels
+// call) for the host and drives it serially: one "thread" per pixel / cell / point in a plain
+// loop.  The not-gpu tests compare it with the oracle to validate the flat layout, the hash
+// directory and the per-node arithmetic before any GPU time is spent.  It is NOT part of the
+// product: libb200tsdf.so has no CPU path and nothing in cpu_tsdf_b200/ loads this library.
+#include "../../cpu_tsdf_b200/csrc/tsdf_core.cuh"
+#include "../../cpu_tsdf_b200/csrc/host_math.h"
+#include "../../cpu_tsdf_b200/csrc/params_setup.h"
+#include "../../oracle/mc_tables.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+using namespace b2;
+
+struct Emu
+{
+  b200tsdf_config cfg;
+  Params p{};
+  std::vector<uint64_t> keys; std::vector<float2> nodes; std::vector<uint32_t> split;
+  std::vector<uchar4> rgb; std::vector<float> M; std::vector<int> ns;
+  std::vector<float2> root_dw; std::vector<uint32_t> root_split; std::vector<uchar4> root_rgb;
+  std::vector<float> root_M; std::vector<int> root_ns;
+  int err = 0;
+  long long n_updates = 0, n_visits = 0, n_culled = 0;
+  std::vector<float> mesh_v; std::vector<unsigned char> mesh_c;
+};
+
+struct Rec { int32_t k[4]; float d, w; uint8_t split, r, g, b; float M; int32_t ns; };
+
+static void collect (const Params& p, const NodePos& n, std::vector<Rec>& out)
+{
+  Rec r; r.k[0] = n.level; r.k[1] = n.x; r.k[2] = n.y; r.k[3] = n.z;
+  float2 dw = *node_dw (p, n);
+  r.d = dw.x; r.w = dw.y; r.r = r.g = r.b = 0; r.M = 0; r.ns = 0;
+  if (n.slot < 0)
+  {
+    if (p.root_rgb) { uchar4 c = p.root_rgb[n.idx]; r.r = c.x; r.g = c.y; r.b = c.z; }
+    if (p.root_M) { r.M = p.root_M[n.idx]; r.ns = p.root_ns[n.idx]; }
+  }
+  else
+  {
+    size_t i = (size_t) n.slot * BRICK_NODES + n.idx;
+    if (p.rgb) { uchar4 c = p.rgb[i]; r.r = c.x; r.g = c.y; r.b = c.z; }
+    if (p.M) { r.M = p.M[i]; r.ns = p.ns[i]; }
+  }
+  bool sp = is_split (p, n);
+  r.split = sp;
+  out.push_back (r);
+  if (!sp) return;
+  int cs = children_slot (p, n, false);
+  if (cs < 0) return;
+  for (int c = 0; c < 8; ++c) collect (p, make_child (p, n, c, cs), out);
+}
+
+extern "C" {
+
+Emu* emu_create (const b200tsdf_config* cfg) { Emu* e = new Emu; e->cfg = *cfg; return e; }
+void emu_destroy (Emu* e) { delete e; }
+
+int emu_reset (Emu* e)
+{
+  size_t pool, root_n;
+  if (derive_params (e->cfg, e->p, pool, root_n)) return -1;
+  Params& p = e->p;
+  e->keys.assign (pool, KEY_EMPTY);
+  e->nodes.assign (pool * BRICK_NODES, make_float2 (-1.f, 0.f));
+  e->split.assign (pool * BRICK_SPLIT_WORDS, 0u);
+  e->root_dw.assign (root_n, make_float2 (-1.f, 0.f));
+  e->root_split.assign ((root_n + 31) / 32, 0u);
+  p.keys = e->keys.data (); p.nodes = e->nodes.data (); p.split = e->split.data ();
+  p.root_dw = e->root_dw.data (); p.root_split = e->root_split.data ();
+  p.rgb = nullptr; p.M = nullptr; p.ns = nullptr; p.root_rgb = nullptr; p.root_M = nullptr; p.root_ns = nullptr;
+  if (p.color)
+  {
+    e->rgb.assign (pool * BRICK_NODES, make_uchar4 (0, 0, 0, 0)); e->root_rgb.assign (root_n, make_uchar4 (0, 0, 0, 0));
+    p.rgb = e->rgb.data (); p.root_rgb = e->root_rgb.data ();
+  }
+  if (p.track_var)
+  {
+    e->M.assign (pool * BRICK_NODES, 0.f); e->ns.assign (pool * BRICK_NODES, 0);
+    e->root_M.assign (root_n, 0.f); e->root_ns.assign (root_n, 0);
+    p.M = e->M.data (); p.ns = e->ns.data (); p.root_M = e->root_M.data (); p.root_ns = e->root_ns.data ();
+  }
+  e->err = 0; p.err = &e->err;
+  if (p.Rtop < p.C)
+  {
+    int n = 1 << p.Rtop;
+    for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z) find_or_insert_brick (p, p.T - 1, x, y, z);
+  }
+  return 0;
+}
+
+int emu_integrate (Emu* e, const void* points, size_t stride, int xyz_off, int rgba_off, int W, int H, const double* pose)
+{
+  const Params& p = e->p;
+  Frame f;
+  f.pts = (const unsigned char*) points; f.stride = (int) stride; f.xyz_off = xyz_off; f.rgba_off = p.color ? rgba_off : -1;
+  f.width = W; f.height = H;
+  double inv[12];
+  b2host::affine_inverse (pose, inv);
+  for (int i = 0; i < 12; ++i) { f.tinv[i] = (float) inv[i]; f.tfwd[i] = (float) pose[i]; }
+  // k_presplit
+  for (int i = 0; i < W * H; ++i)
+  {
+    int u = i % W, v = i / W;
+    const float* pt = frame_xyz (f, u, v);
+    if (is_nan (pt[2])) continue;
+    float pw[3];
+    affine_mul_f (f.tfwd, pt[0], pt[1], pt[2], pw);
+    int fx_, fy_, fz_;
+    if (!world_to_finest (p, pw[0], pw[1], pw[2], fx_, fy_, fz_)) continue;
+    int sh = p.L - p.C;
+    if (!owns_cell (p, fx_ >> sh, fy_ >> sh, fz_ >> sh)) continue;
+    presplit_point (p, fx_, fy_, fz_);
+  }
+  // k_cull + k_update_dfs
+  float pl[6][4];
+  b2host::frustum_planes (pose, p.width, p.height, p.fx, p.fy, p.min_sensor, p.max_sensor, pl);
+  int n = 1 << p.C;
+  Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
+  e->n_culled = 0;
+  for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z)
+  {
+    if (!frustum_contains (pl, center1d (p, p.C, x), center1d (p, p.C, y), center1d (p, p.C, z))) continue;
+    if (!owns_cell (p, x, y, z)) continue;
+    e->n_culled++;
+    NodePos nd;
+    if (!locate_node (p, p.C, x, y, z, nd)) return -2;
+    update_voxel_dfs (p, f, nd, cnt);
+  }
+  e->n_updates = cnt.n_updates; e->n_visits = cnt.n_visits;
+  return e->err;
+}
+
+void emu_stats (const Emu* e, long long* out3) { out3[0] = e->n_updates; out3[1] = e->n_visits; out3[2] = e->n_culled; }
+
+long long emu_dump_nodes (const Emu* e, int32_t* keys, float* dw, uint8_t* flags, uint8_t* rgb, float* M, int32_t* ns)
+{
+  const Params& p = e->p;
+  std::vector<Rec> recs;
+  int n = 1 << p.C;
+  for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z)
+  {
+    NodePos nd;
+    if (!locate_node (p, p.C, x, y, z, nd)) return -1;
+    collect (p, nd, recs);
+  }
+  if (!keys && !dw && !flags && !rgb && !M && !ns) return (long long) recs.size ();
+  std::sort (recs.begin (), recs.end (), [] (const Rec& a, const Rec& b) { return std::lexicographical_compare (a.k, a.k + 4, b.k, b.k + 4); });
+  for (size_t i = 0; i < recs.size (); ++i)
+  {
+    const Rec& r = recs[i];
+    if (keys) std::memcpy (keys + 4 * i, r.k, 16);
+    if (dw) { dw[2 * i] = r.d; dw[2 * i + 1] = r.w; }
+    if (flags) flags[i] = r.split;
+    if (rgb) { rgb[3 * i] = r.r; rgb[3 * i + 1] = r.g; rgb[3 * i + 2] = r.b; }
+    if (M) M[i] = r.M;
+    if (ns) ns[i] = r.ns;
+  }
+  return (long long) recs.size ();
+}
+
+int emu_query (const Emu* e, const float* xyz, int n, int what, int mode, float* val, float* grad, float* hess, uint8_t* ok)
+{
+  for (int i = 0; i < n; ++i)
+  {
+    float v, g[3], hs[9];
+    bool good = query_point (e->p, xyz + 3 * i, mode, &v, g, hs);
+    ok[i] = good;
+    if (!good) continue;
+    if (what & 1) val[i] = v;
+    if (what & 2) { grad[3 * i] = g[0]; grad[3 * i + 1] = g[1]; grad[3 * i + 2] = g[2]; }
+    if (what & 4) for (int k = 0; k < 9; ++k) hess[9 * i + k] = hs[k];
+  }
+  return 0;
+}
+
+int emu_render (const Emu* e, const double* pose, int downsample, void* out, size_t stride, int xyz_off, int normal_off, uint8_t* rgb_out)
+{
+  RenderParams r;
+  make_render_params (e->cfg, e->p, pose, downsample, r);
+  unsigned char* base = (unsigned char*) out;
+  for (int y = 0; y < r.height; ++y) for (int x = 0; x < r.width; ++x)
+  {
+    size_t i = (size_t) y * r.width + x;
+    float P[3], N[3];
+    render_pixel (e->p, r, x, y, P, N, rgb_out ? rgb_out + 3 * i : nullptr);
+    std::memcpy (base + i * stride + xyz_off, P, 12);
+    std::memcpy (base + i * stride + normal_off, N, 12);
+  }
+  return 0;
+}
+
+long long emu_mesh (Emu* e, float w_min, int color_mode, const float** verts, const uint8_t** cols)
+{
+  const Params& p = e->p;
+  McParams mc;
+  make_mc_params (e->cfg, p, w_min, color_mode, mc);
+  std::vector<Rec> recs;
+  e->mesh_v.clear (); e->mesh_c.clear ();
+  // every leaf, any level (order is irrelevant: tests compare sorted soups)
+  int n = 1 << p.C;
+  std::vector<NodePos> stack;
+  for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z)
+  {
+    NodePos nd;
+    if (!locate_node (p, p.C, x, y, z, nd)) return -1;
+    stack.push_back (nd);
+    while (!stack.empty ())
+    {
+      NodePos q = stack.back (); stack.pop_back ();
+      if (is_split (p, q))
+      {
+        int cs = children_slot (p, q, false);
+        for (int c = 0; c < 8 && cs >= 0; ++c) stack.push_back (make_child (p, q, c, cs));
+        continue;
+      }
+      float2 dw = *node_dw (p, q);
+      float v[45]; unsigned char cc[45];
+      int nt = mc_leaf (p, mc, q, dw.x, dw.y, mc_tables::edge_table, mc_tables::tri_table, v, color_mode ? cc : nullptr);
+      for (int i = 0; i < 9 * nt; ++i) { e->mesh_v.push_back (v[i]); if (color_mode) e->mesh_c.push_back (cc[i]); }
+    }
+  }
+  *verts = e->mesh_v.data ();
+  if (cols) *cols = color_mode ? e->mesh_c.data () : nullptr;
+  return (long long) (e->mesh_v.size () / 3);
+}
+
+int emu_levels (const Emu* e, int* out4) { out4[0] = e->p.C; out4[1] = e->p.L; out4[2] = e->p.T; out4[3] = e->p.Rtop; return 0; }
+
+int emu_frustum_cull (const Emu* e, const double* pose, uint8_t* mask)
+{
+  const Params& p = e->p;
+  float pl[6][4];
+  b2host::frustum_planes (pose, p.width, p.height, p.fx, p.fy, p.min_sensor, p.max_sensor, pl);
+  int n = 1 << p.C, kept = 0;
+  for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z)
+  {
+    bool in = frustum_contains (pl, center1d (p, p.C, x), center1d (p, p.C, y), center1d (p, p.C, z));
+    mask[((size_t) x * n + y) * n + z] = in; kept += in;
+  }
+  return kept;
+}
+
+} // extern "C"

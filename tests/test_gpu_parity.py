@@ -1,0 +1,209 @@
+"""CUDA engine (through the C ABI / Python mirror) vs the CPU oracle on a real B200.
+
+Bar (north_star): per-voxel {sdf,weight} and mesh vertices within a stated float tolerance,
+renderView depth within 1e-4 m.  The engine reproduces the reference's arithmetic expression by
+expression, so the tests demand BIT-EXACT equality at every node of every octree level, on every
+render pixel and on every mesh vertex; the tolerances of the north star are upper bounds."""
+import os
+
+import numpy as np
+import pytest
+
+import cpu_tsdf_b200 as pkg
+from cpu_tsdf_b200 import synth
+from oracle.oracle_py import OracleVolume
+from tests.common import CAM, CFG_256, CFG_512, CFG_2048, assert_same_nodes, canon_soup, frames, query_points
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(cfg, pool_log2=17, **kw):
+    v = pkg.TSDFVolumeOctree(device=0, pool_log2=pool_log2, track_variance=bool(kw.pop("track_variance", 0)))
+    v.setResolution(cfg["xres"], cfg["yres"], cfg["zres"])
+    v.setGridSize(cfg.get("xsize", 3.0), cfg.get("ysize", 3.0), cfg.get("zsize", 3.0))
+    v.setCameraIntrinsics(cfg.get("fx", 525.0), cfg.get("fy", 525.0), cfg["cx"], cfg["cy"])
+    if "max_cell_x" in cfg:
+        v.setMaxVoxelSize(cfg["max_cell_x"], cfg["max_cell_y"], cfg["max_cell_z"])
+    if kw.get("integrate_color"):
+        v.setIntegrateColor(True)
+    if "max_weight" in kw:
+        v.setWeightTruncationLimit(kw["max_weight"])
+    if "global_transform" in kw:
+        v.setGlobalTransform(kw["global_transform"])
+    v.reset()
+    return v
+
+
+def pair(cfg, pool_log2=17, **kw):
+    o = OracleVolume(**cfg, **{k: v for k, v in kw.items() if k != "track_variance"})
+    o.reset()
+    return o, make_engine(cfg, pool_log2, **kw)
+
+
+def test_engine_library_is_the_cuda_one(engine_lib):
+    # the path under test is the in-tree CUDA library; nothing else implements the ABI
+    assert os.path.samefile(engine_lib, pkg.LIB_PATH)
+    maps = open("/proc/self/maps").read()
+    make_engine(CFG_256, 12)
+    assert "libb200tsdf.so" in open("/proc/self/maps").read() or "libb200tsdf.so" in maps
+
+
+def test_single_frame_256_exact():
+    o, e = pair(CFG_256)
+    pose = synth.orbit_pose(synth.S1, 0, 1)
+    cloud = synth.make_frame(synth.S1, pose, CAM)
+    o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
+    st = e.stats()
+    assert st.n_updates == o.stats().n_add_observation == 175900
+    assert st.n_culled_cells == o.stats().n_culled_cells
+
+
+def test_multi_frame_noise_color_variance_256():
+    o, e = pair(CFG_256, integrate_color=1, track_variance=1)
+    for pose, cloud in frames(synth.S1, 6, stride=9, color=True, noise_seed=11, dropout=0.02):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+        assert e.stats().n_updates == o.stats().n_add_observation
+    assert_same_nodes(o.dump_nodes(), e.download_nodes(), rgb=True, var=True)
+
+
+def test_orbit_512_config2():
+    o, e = pair(CFG_512, 18)
+    for pose, cloud in frames(synth.S1, 10, stride=10, noise_seed=2):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
+    for f in (0, 25, 50, 75):
+        pose = synth.orbit_pose(synth.S1, f, 100)
+        ra = o.render(pose, 2); rb = e.renderView(pose, 2)
+        good = np.isfinite(ra[..., 2])
+        assert good.sum() > 20000
+        assert np.array_equal(np.isfinite(rb[..., 2]), good)
+        assert np.nanmax(np.abs(ra[..., 2] - rb[..., 2])) <= 1e-4        # north-star bar
+        assert np.array_equal(ra[..., :3], rb[..., :3], equal_nan=True)   # what we actually hold
+        assert np.array_equal(ra[..., 4:7], rb[..., 4:7], equal_nan=True)
+
+
+def test_interior_2048_config3_color_mesh():
+    o, e = pair(CFG_2048, 18, integrate_color=1)
+    for pose, cloud in frames(synth.S2, 4, stride=2, color=True, noise_seed=4):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+        assert e.stats().n_updates == o.stats().n_add_observation
+    assert_same_nodes(o.dump_nodes(), e.download_nodes(), rgb=True)
+    mc = pkg.MarchingCubesTSDFOctree()
+    mc.setInputTSDF(e)
+    for wmin, rgb in ((2.0, True), (0.0, False)):
+        mc.setMinWeight(wmin); mc.setColorByRGB(rgb)
+        vb, cb, polys = mc.reconstruct()
+        va, ca = o.mesh(wmin, 1 if rgb else 0)
+        assert len(va) == len(vb) > 10000 and len(polys) * 3 == len(vb)
+        assert np.array_equal(canon_soup(va, ca), canon_soup(vb, cb))
+        assert np.abs(canon_soup(va)[:, :9] - canon_soup(vb)[:, :9]).max() <= 1e-5   # north-star bar
+
+
+@pytest.mark.parametrize("res,size,cell", [(128, 3.0, 0.5), (1024, 3.0, 0.5), (256, 2.7, 0.3), (512, 12.0, 0.5)])
+def test_other_tier_shapes(res, size, cell):
+    cfg = dict(xres=res, yres=res, zres=res, xsize=size, ysize=size, zsize=size, cx=CAM.cx, cy=CAM.cy,
+               max_cell_x=cell, max_cell_y=cell, max_cell_z=cell)
+    o, e = pair(cfg)
+    scene = synth.Scene(room_half=min(1.3, size * 0.45), cam_radius=0.8)
+    for pose, cloud in frames(scene, 2, stride=6, noise_seed=9):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
+
+
+def test_edge_cases_empty_nan_and_out_of_volume():
+    o, e = pair(CFG_256)
+    pose = synth.orbit_pose(synth.S1, 0, 1)
+    empty = np.full((CAM.height, CAM.width, 4), np.nan, np.float32)
+    o.integrate(empty, pose); e.integrateCloud(empty, None, pose)
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
+    assert e.stats().n_updates == 0
+    big = synth.Scene(room_half=4.0, cam_radius=1.0)
+    cloud = synth.make_frame(big, pose, CAM)
+    o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    outside = np.eye(4); outside[:3, 3] = (5.0, 0.0, 0.0)
+    cloud = synth.make_frame(synth.S1, outside, CAM)
+    o.integrate(cloud, outside); e.integrateCloud(cloud, None, outside)
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
+
+
+def test_weight_saturation_and_reset_idempotence():
+    o, e = pair(CFG_256, max_weight=3)
+    pose = synth.orbit_pose(synth.S1, 0, 1)
+    cloud = synth.make_frame(synth.S1, pose, CAM, noise_seed=1)
+    for _ in range(5):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    a = e.download_nodes()
+    assert_same_nodes(o.dump_nodes(), a)
+    assert a["dw"][:, 1].max() == 3.0
+    e.reset(); o.reset()
+    b = e.download_nodes()
+    assert len(b["keys"]) == 512 and (b["dw"] == [-1, 0]).all()
+    o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
+
+
+def test_frustum_cull_mask():
+    o, e = pair(CFG_2048, 12)
+    for f in (0, 17, 33, 71):
+        for scene in (synth.S1, synth.S2):
+            pose = synth.orbit_pose(scene, f, 100)
+            ma, ka = o.frustum_cull(pose)
+            mb = e.getFrustumCulledVoxels(pose)
+            assert ka == mb.sum() and np.array_equal(ma.astype(bool), mb)
+
+
+def test_queries_render_mesh_256():
+    o, e = pair(CFG_256, integrate_color=1)
+    for pose, cloud in frames(synth.S1, 5, stride=7, color=True, noise_seed=5):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    pts = query_points()
+    for mode, fn in ((0, None), (1, None)):
+        a = o.query(pts, 7, mode)
+        b = e._query(pts, 7, mode)
+        assert np.array_equal(a[3], b[3]) and a[3].sum() > 1000
+        for k in range(3):
+            assert np.array_equal(a[k][a[3]].view(np.uint32), b[k][b[3]].view(np.uint32))
+    ok, val = e.getFxn(pts[0])
+    assert isinstance(ok, bool)
+    pose = synth.orbit_pose(synth.S1, 10, 100)
+    ra, ca = o.render(pose, 1, colored=True)
+    rb, cb = e.renderColoredView(pose, 1)
+    assert np.isfinite(ra[..., 2]).sum() > 100000
+    assert np.array_equal(ra[..., :3], rb[..., :3], equal_nan=True)
+    assert np.array_equal(ra[..., 4:7], rb[..., 4:7], equal_nan=True)
+    assert np.array_equal(ca, cb)
+    mc = pkg.MarchingCubesTSDFOctree(); mc.setInputTSDF(e)
+    for cm, wmin in ((0, 2.0), (1, 0.0), (2, 2.5)):
+        mc.setMinWeight(wmin); mc.setColorByRGB(cm == 1); mc.setColorByConfidence(cm == 2)
+        vb, colb, _ = mc.reconstruct()
+        va, cola = o.mesh(wmin, cm)
+        assert len(va) == len(vb) > 3000
+        assert np.array_equal(canon_soup(va, cola), canon_soup(vb, colb))
+
+
+def test_save_vol_matches_oracle_bytes(tmp_path):
+    o, e = pair(CFG_256, integrate_color=1, track_variance=1)
+    for pose, cloud in frames(synth.S1, 3, stride=7, color=True, noise_seed=5):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    pa, pb = str(tmp_path / "a.vol"), str(tmp_path / "b.vol")
+    assert o.save(pa) == 0
+    e.save(pb)
+    assert open(pa, "rb").read() == open(pb, "rb").read()
+
+
+def test_errors_are_reported_not_thrown():
+    v = pkg.TSDFVolumeOctree(device=0, pool_log2=12)
+    with pytest.raises(pkg.B200Error):
+        v.integrateCloud(np.zeros((4, 4, 4), np.float32), None, np.eye(4))     # before reset()
+    v.setResolution(100, 100, 100)
+    with pytest.raises(pkg.B200Error):
+        v.reset()                                                              # not a power of two
+    v.setResolution(256, 256, 256); v.reset()
+    # a pool that is too small must surface as ENOMEM, not corrupt memory
+    small = pkg.TSDFVolumeOctree(device=0, pool_log2=8)
+    small.setResolution(512, 512, 512); small.setCameraIntrinsics(525, 525, CAM.cx, CAM.cy); small.reset()
+    pose = synth.orbit_pose(synth.S1, 0, 1)
+    with pytest.raises(pkg.B200Error):
+        small.integrateCloud(synth.make_frame(synth.S1, pose, CAM), None, pose)
+        small.sync()
