@@ -7,6 +7,7 @@
 #include "mc_tables.cuh"
 #include "host_math.h"
 #include "params_setup.h"
+#include "brick_kernels.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -83,7 +84,7 @@ __global__ void k_presplit (Params p, Frame f)
 }
 
 // frustum cull of the coarse cells (tsdf_volume_octree.cpp:619-652); planes come from the host
-__global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restrict__ count, unsigned char* __restrict__ mask)
+__global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restrict__ count, unsigned char* __restrict__ mask, QNode* __restrict__ q0)
 {
   int n = 1 << p.C;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,7 +93,18 @@ __global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restr
   float cx = center1d (p, p.C, x), cy = center1d (p, p.C, y), cz = center1d (p, p.C, z);
   bool in = frustum_contains (P.pl, cx, cy, cz);
   if (mask) mask[i] = in ? 1 : 0;
-  if (in && list && owns_cell (p, x, y, z)) list[atomicAdd (count, 1)] = i;
+  if (in && list && owns_cell (p, x, y, z))
+  {
+    int k = atomicAdd (count, 1);
+    list[k] = i;
+    if (q0)
+    {
+      NodePos n;
+      if (!locate_node (p, p.C, x, y, z, n)) { raise_err (p, ERR_MISSING_BRICK); n.slot = -1; n.idx = 0; }
+      QNode e; e.x = x; e.y = y; e.z = z; e.slot = n.slot; e.idx = n.idx; e.kind = KIND_DONE; e.child_base = -1; e.rc = 0;
+      q0[k] = e;
+    }
+  }
 }
 
 // general path: one thread per culled coarse cell runs updateVoxel depth-first
@@ -270,6 +282,9 @@ struct b200tsdf
   size_t culled_cap = 0;
   bool timed = false;
   bool is_empty = true;          // TSDFVolumeOctree::is_empty_ (cpp:205, hpp:101)
+  // fast-path work queues (levels C .. L-3)
+  Queues Q{}; int q_levels = 0; QNode* q_mem = nullptr; size_t q_mem_cap = 0;
+  bool fast_path = false; int force_general = 0;
   // measurement
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
   cudaEvent_t kring[KRING][2] = {};
@@ -370,7 +385,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
   free_volume (h);
   cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled);
-  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]);
+  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
   if (h->ev_k0) cudaEventDestroy (h->ev_k0); if (h->ev_k1) cudaEventDestroy (h->ev_k1);
@@ -435,6 +450,31 @@ int b200tsdf_reset (b200tsdf_t* h)
     CK (cudaMalloc (&h->d_culled, ncells * sizeof (int)));
     h->culled_cap = ncells;
   }
+  {
+    // work queues for levels C .. B = L-3 (fast path needs the block-root level at or below the coarse depth)
+    int Bl = np.L - 3;
+    h->force_general = c.reserved[0] & 1;
+    h->fast_path = (Bl >= np.C) && !var && !h->force_general && (Bl - np.C + 1 <= MAX_QLEVELS);
+    h->q_levels = h->fast_path ? (Bl - np.C + 1) : 0;
+    size_t total = 0; size_t caps[MAX_QLEVELS] = {};
+    for (int i = 0; i < h->q_levels; ++i)
+    {
+      int lv = np.C + i;
+      size_t full = lv >= 7 ? ((size_t) 1 << 21) : ((size_t) 1 << (3 * lv));
+      caps[i] = std::min (full, (size_t) 1 << 21);
+      total += caps[i];
+    }
+    if (total > h->q_mem_cap)
+    {
+      cudaFree (h->q_mem); h->q_mem = nullptr; h->q_mem_cap = 0;
+      CK (cudaMalloc (&h->q_mem, total * sizeof (QNode)));
+      h->q_mem_cap = total;
+    }
+    size_t off = 0;
+    for (int i = 0; i < MAX_QLEVELS; ++i) { h->Q.q[i] = nullptr; h->Q.cap[i] = 0; }
+    for (int i = 0; i < h->q_levels; ++i) { h->Q.q[i] = h->q_mem + off; h->Q.cap[i] = (int) caps[i]; off += caps[i]; }
+    h->Q.n = h->d_count;
+  }
   Params& p = h->p;
   {
     // keep the storage pointers, take every scalar from the derived set
@@ -482,16 +522,32 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   int npix = W * H;
   k_presplit<<<(npix + 255) / 256, 256, 0, s>>> (p, f);
   int ncells = 1 << (3 * p.C);
-  k_cull<<<(ncells + 127) / 128, 128, 0, s>>> (p, P, h->d_culled, h->d_count, nullptr);
+  k_cull<<<(ncells + 127) / 128, 128, 0, s>>> (p, P, h->d_culled, h->d_count, nullptr, h->fast_path ? h->Q.q[0] : nullptr);
+  h->launches += 3;
   // dominant kernel, bracketed by a ring of event pairs so bench.py can average its launch duration
   if (h->kring_pending >= KRING) h->drain_kring (KRING / 2);
   int kr = h->kring_head;
-  CK (cudaEventRecord (h->kring[kr][0], s));
-  // general path: every culled cell depth-first (grid covers the worst case; threads past *count exit)
-  k_update_dfs<<<(ncells + 31) / 32, 32, 0, s>>> (p, f, h->d_culled, h->d_count, h->d_stats);
-  CK (cudaEventRecord (h->kring[kr][1], s));
+  if (h->fast_path)
+  {
+    const int nl = h->q_levels;
+    for (int li = 0; li < nl - 1; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
+    CK (cudaEventRecord (h->kring[kr][0], s));
+    if (p.color) k_blocks<true><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_stats);
+    else k_blocks<false><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_stats);
+    CK (cudaEventRecord (h->kring[kr][1], s));
+    h->launches++;
+    for (int li = nl - 2; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
+  }
+  else
+  {
+    CK (cudaEventRecord (h->kring[kr][0], s));
+    // general path: every culled cell depth-first (grid covers the worst case; threads past *count exit)
+    k_update_dfs<<<(ncells + 31) / 32, 32, 0, s>>> (p, f, h->d_culled, h->d_count, h->d_stats);
+    CK (cudaEventRecord (h->kring[kr][1], s));
+    h->launches++;
+  }
   h->kring_head = (kr + 1) % KRING; h->kring_pending++;
-  h->launches += 4; h->prof_frames++;
+  h->prof_frames++;
   CK (cudaEventRecord (h->ev_t1, s));
   CK (cudaGetLastError ());
   h->timed = true;
@@ -718,7 +774,7 @@ int b200tsdf_frustum_cull (b200tsdf_t* h, const double* pose, uint8_t* mask, int
   int ncells = 1 << (3 * p.C);
   unsigned char* d_mask = nullptr;
   CK (cudaMalloc (&d_mask, ncells));
-  k_cull<<<(ncells + 127) / 128, 128, 0, h->stream>>> (p, P, nullptr, nullptr, d_mask);
+  k_cull<<<(ncells + 127) / 128, 128, 0, h->stream>>> (p, P, nullptr, nullptr, d_mask, nullptr);
   CK (cudaMemcpyAsync (mask, d_mask, ncells, cudaMemcpyDeviceToHost, h->stream));
   CK (cudaStreamSynchronize (h->stream));
   cudaFree (d_mask);

@@ -443,9 +443,10 @@ B2_HD Obs observe (const Params& p, const Frame& f, float cx, float cy, float cz
   return o;
 }
 
-// truncation + addObservation + return code (hpp:189-214, octree.cpp:152-163, :328-337).
-// Returns 1 / 0 / -1 like updateVoxel; `updated` says whether the stored state changed.
-B2_HD int leaf_update (const Params& p, const Frame& f, const NodePos& n, const Obs& o, bool& updated)
+// truncation + addObservation + return code (hpp:189-214, octree.cpp:152-163, :328-337) on VALUES:
+// dw / c / M / ns are the node's state (in registers, shared memory or wherever the caller staged
+// it).  Returns 1 / 0 / -1 like updateVoxel; `updated` says whether the state changed.
+B2_HD int leaf_update_values (const Params& p, const Frame& f, const Obs& o, float2& dw, uchar4& c, float& M, int& ns, bool& updated)
 {
   updated = false;
   float d_new = o.d_new;
@@ -453,38 +454,54 @@ B2_HD int leaf_update (const Params& p, const Frame& f, const NodePos& n, const 
   else if (d_new < -p.max_dist_neg) return 0;
   d_new = fdiv (d_new, p.max_dist_neg);
   const float w_new = 1.f;
-  float2* dwp = node_dw (p, n);
-  float2 dw = *dwp;
-  if (p.color)
+  if (p.color && f.rgba_off >= 0)
   {
-    uchar4* cp = n.slot < 0 ? &p.root_rgb[n.idx] : &p.rgb[(size_t) n.slot * BRICK_NODES + n.idx];
-    uchar4 c = *cp;
-    if (f.rgba_off >= 0)
-    {
-      const unsigned char* bgr = frame_bgr (f, o.u, o.v);
-      float wsum = fadd (dw.y, w_new);
-      c.x = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.x), fmul (w_new, (float) bgr[2])), wsum);   // r
-      c.y = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.y), fmul (w_new, (float) bgr[1])), wsum);   // g
-      c.z = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.z), fmul (w_new, (float) bgr[0])), wsum);   // b
-      *cp = c;
-    }
+    const unsigned char* bgr = frame_bgr (f, o.u, o.v);
+    float wsum = fadd (dw.y, w_new);
+    c.x = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.x), fmul (w_new, (float) bgr[2])), wsum);   // r
+    c.y = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.y), fmul (w_new, (float) bgr[1])), wsum);   // g
+    c.z = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.z), fmul (w_new, (float) bgr[0])), wsum);   // b
   }
   float d_old = dw.x;
   float d = fdiv (fadd (fmul (dw.x, dw.y), fmul (d_new, w_new)), fadd (dw.y, w_new));
   float w = fadd (dw.y, w_new);
   if (w > p.max_weight) w = p.max_weight;
-  *dwp = make_float2 (d, w);
+  dw = make_float2 (d, w);
   if (p.track_var)
   {
-    float* Mp = n.slot < 0 ? &p.root_M[n.idx] : &p.M[(size_t) n.slot * BRICK_NODES + n.idx];
-    int* np = n.slot < 0 ? &p.root_ns[n.idx] : &p.ns[(size_t) n.slot * BRICK_NODES + n.idx];
-    *Mp = fadd (*Mp, fmul (fmul (w_new, fsub (d_new, d)), fsub (d_new, d_old)));
-    *np = *np + 1;
+    M = fadd (M, fmul (fmul (w_new, fsub (d_new, d)), fsub (d_new, d_old)));
+    ns = ns + 1;
   }
   updated = true;
   if ((double) d < -0.99) return 0;
   else if ((double) d < p.rc_thresh) return 1;
   else return -1;
+}
+
+// the same on a node in global storage
+B2_HD int leaf_update (const Params& p, const Frame& f, const NodePos& n, const Obs& o, bool& updated)
+{
+  float2* dwp = node_dw (p, n);
+  float2 dw = *dwp;
+  uchar4 c = make_uchar4 (0, 0, 0, 0);
+  uchar4* cp = nullptr;
+  if (p.color) { cp = n.slot < 0 ? &p.root_rgb[n.idx] : &p.rgb[(size_t) n.slot * BRICK_NODES + n.idx]; c = *cp; }
+  float M = 0.f; int ns = 0;
+  float* Mp = nullptr; int* np = nullptr;
+  if (p.track_var)
+  {
+    Mp = n.slot < 0 ? &p.root_M[n.idx] : &p.M[(size_t) n.slot * BRICK_NODES + n.idx];
+    np = n.slot < 0 ? &p.root_ns[n.idx] : &p.ns[(size_t) n.slot * BRICK_NODES + n.idx];
+    M = *Mp; ns = *np;
+  }
+  int rc = leaf_update_values (p, f, o, dw, c, M, ns, updated);
+  if (updated)
+  {
+    *dwp = dw;
+    if (cp) *cp = c;
+    if (Mp) { *Mp = M; *np = ns; }
+  }
+  return rc;
 }
 
 struct Counters { long long n_updates, n_visits; };
