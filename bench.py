@@ -292,7 +292,8 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "kernel": "brick update (k_update_*)",
                 "bytes_per_launch": b_alg_local / max(1, prof.kernel_launches),
                 "us_per_launch": 1e3 * prof.ms_kernel / max(1, prof.kernel_launches),
-                "updates_per_frame": prof.n_updates / max(1, prof.n_frames)}
+                "updates_per_frame": prof.n_updates / max(1, prof.n_frames),
+                "blocks_last_frame": int(vol.stats().n_block_visits), "bricks_allocated": int(vol.stats().n_bricks)}
 
     if rank == 0:
         cpu = None

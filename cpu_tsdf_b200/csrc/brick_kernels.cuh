@@ -49,9 +49,19 @@ __device__ __forceinline__ NodePos qnode_pos (const Params& p, int level, const 
   return n;
 }
 
-__device__ __forceinline__ bool push_children (const Params& p, const Queues& Q, int li, const NodePos& n, int cs, QNode& e)
+// Appends the 8 children of `n` to the next level's queue.  Called by every lane of the warp with
+// `want` saying whether this lane pushes: one atomicAdd per warp reserves the whole range.
+__device__ __forceinline__ bool push_children (const Params& p, const Queues& Q, int li, bool want, const NodePos& n, int cs, QNode& e)
 {
-  int base = atomicAdd (&Q.n[li + 1], 8);
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned mask = __ballot_sync (0xffffffffu, want);
+  if (!mask) return false;
+  int base = 0;
+  const int leader = __ffs (mask) - 1;
+  if ((int) lane == leader) base = atomicAdd (&Q.n[li + 1], 8 * __popc (mask));
+  base = __shfl_sync (0xffffffffu, base, leader);
+  if (!want) return false;
+  base += 8 * __popc (mask & ((1u << lane) - 1));
   if (base + 8 > Q.cap[li + 1]) { raise_err (p, ERR_QUEUE_FULL); e.kind = KIND_DONE; e.rc = 0; return false; }
   e.child_base = base;
   for (int c = 0; c < 8; ++c)
@@ -63,51 +73,93 @@ __device__ __forceinline__ bool push_children (const Params& p, const Queues& Q,
   return true;
 }
 
+__device__ __forceinline__ void warp_add_stats (unsigned long long* stats, unsigned long long upd, unsigned long long vis)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    upd += __shfl_down_sync (0xffffffffu, upd, o);
+    vis += __shfl_down_sync (0xffffffffu, vis, o);
+  }
+  if ((threadIdx.x & 31) == 0)
+  {
+    if (upd) atomicAdd (&stats[0], upd);
+    if (vis) atomicAdd (&stats[1], vis);
+  }
+}
+
 // ---- 1. top-down over the upper levels: one thread per queued node ---------------------------------
-__global__ void k_upper_down (Params p, Frame f, Queues Q, int li, unsigned long long* __restrict__ stats)
+// `block_level`: the queue holds block roots (level L-3); interior ones go to the block list with their
+// brick slot instead of having their children queued.
+__global__ void k_upper_down (Params p, Frame f, Queues Q, int li, int block_level, int* __restrict__ blist, int* __restrict__ bcount,
+                              unsigned long long* __restrict__ stats)
 {
   int level = p.C + li;
   int count = Q.n[li];
   if (count > Q.cap[li]) count = Q.cap[li];
   unsigned long long upd = 0, vis = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+  const int stride = gridDim.x * blockDim.x;
+  const int rounds = (count + stride - 1) / stride;                 // warp-uniform trip count (the pushes use warp collectives)
+  for (int r = 0; r < rounds; ++r)
   {
-    QNode e = Q.q[li][i];
-    NodePos n = qnode_pos (p, level, e);
-    vis++;
-    uint32_t m; uint32_t* sw = split_word (p, n, m);
-    if (*sw & m)                                                    // hpp:122
+    const int i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < count;
+    QNode e; NodePos n; int cs = -1;
+    bool push = false, to_blocks = false;
+    e.kind = KIND_DONE; e.rc = 0; e.child_base = -1;
+    if (active)
     {
-      int cs = children_slot (p, n, false);
-      if (cs < 0) { raise_err (p, ERR_MISSING_BRICK); e.kind = KIND_DONE; e.rc = 0; }
-      else { e.kind = KIND_OLD; push_children (p, Q, li, n, cs, e); }
-    }
-    else
-    {
-      Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
-      if (!o.valid) { e.kind = KIND_DONE; e.rc = 0; }
-      else if (o.near_ && n.size > p.finest_size)                    // hpp:161-166
+      e = Q.q[li][i];
+      n = qnode_pos (p, level, e);
+      vis++;
+      uint32_t m; uint32_t* sw = split_word (p, n, m);
+      if (*sw & m)                                                    // hpp:122
       {
-        int cs = children_slot (p, n, true);
-        if (cs < 0) { e.kind = KIND_DONE; e.rc = 0; }
-        else
-        {
-          e.kind = KIND_NEW;
-          if (push_children (p, Q, li, n, cs, e)) atomicOr (sw, m);   // split (): children are fresh by invariant
-        }
+        cs = children_slot (p, n, false);
+        if (cs < 0) { raise_err (p, ERR_MISSING_BRICK); e.kind = KIND_DONE; e.rc = 0; }
+        else { e.kind = KIND_OLD; push = !block_level; to_blocks = block_level; }
       }
       else
       {
-        bool updated;
-        e.rc = leaf_update (p, f, n, o, updated);
-        e.kind = KIND_DONE;
-        upd += updated;
+        Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
+        if (!o.valid) { e.kind = KIND_DONE; e.rc = 0; }
+        else if (o.near_ && n.size > p.finest_size)                    // hpp:161-166
+        {
+          cs = children_slot (p, n, true);
+          if (cs < 0) { e.kind = KIND_DONE; e.rc = 0; }
+          else
+          {
+            e.kind = KIND_NEW; push = !block_level; to_blocks = block_level;
+            atomicOr (sw, m);                                          // split (): children are fresh by invariant
+          }
+        }
+        else
+        {
+          bool updated;
+          e.rc = leaf_update (p, f, n, o, updated);
+          e.kind = KIND_DONE;
+          upd += updated;
+        }
       }
     }
-    Q.q[li][i] = e;
+    if (!block_level) push_children (p, Q, li, push, n, cs, e);
+    else
+    {
+      // interior block roots go to the block list (one atomic per warp)
+      const unsigned lane = threadIdx.x & 31;
+      const unsigned mask = __ballot_sync (0xffffffffu, to_blocks);
+      if (mask)
+      {
+        int base = 0;
+        const int leader = __ffs (mask) - 1;
+        if ((int) lane == leader) base = atomicAdd (bcount, __popc (mask));
+        base = __shfl_sync (0xffffffffu, base, leader);
+        if (to_blocks) { e.child_base = cs; blist[base + __popc (mask & ((1u << lane) - 1))] = i; }
+      }
+    }
+    if (active) Q.q[li][i] = e;
   }
-  if (upd) atomicAdd (&stats[0], upd);
-  if (vis) atomicAdd (&stats[1], vis);
+  warp_add_stats (stats, upd, vis);
 }
 
 // ---- 3. bottom-up over the upper levels -------------------------------------------------------------
@@ -150,153 +202,158 @@ __global__ void k_upper_up (Params p, Frame f, Queues Q, int li, unsigned long l
     e.kind = KIND_DONE;
     Q.q[li][i].rc = e.rc;
   }
-  if (upd) atomicAdd (&stats[0], upd);
-  if (vis) atomicAdd (&stats[1], vis);
+  __syncwarp ();
+  warp_add_stats (stats, upd, vis);
 }
 
-// ---- 2. one warp per block root -----------------------------------------------------------------------
+// ---- 2. one warp per interior block root ------------------------------------------------------------------
+// Block roots (level B = L-3) are evaluated by k_upper_down like every other upper node; only the
+// ones that have (or get) children are appended to the block list, with the brick slot cached in
+// QNode::child_base.  Each warp stages one brick (8 + 64 + 512 nodes, 4.7 KB, + 2.3 KB colour) in
+// shared memory, runs updateVoxel's top-down and bottom-up passes over it with ballots, and writes
+// back only what changed.
 constexpr int BLK_WARPS = 4;
 
 struct WarpSmem
 {
   float2 dw[BRICK_NODES];       // 4672 B
   uchar4 rgb[BRICK_NODES];      // 2336 B (colour volumes only)
+  float dnew[72];               // saved observation of level-1/2 nodes split this frame (fall-through update)
+  int uv[72];
 };
 
-__device__ __forceinline__ void child_center (float pc, float off, int bit, float& c)
-{ c = bit ? fadd (pc, off) : fsub (pc, off); }
-
-// process the node held at smem index `si`, geometry (cx,cy,cz,size); returns rc, sets flags
-struct NodeResult { int kind; int rc; bool updated; Obs o; };
-
-__device__ __forceinline__ NodeResult visit_node (const Params& p, const Frame& f, WarpSmem& S, int si, bool split_old,
-                                                  float cx, float cy, float cz, float size, bool can_split)
+__device__ __forceinline__ void path_center (const float* c0, float off, int k, int j, float* c)
 {
-  NodeResult r; r.kind = KIND_DONE; r.rc = 0; r.updated = false;
-  if (split_old) { r.kind = KIND_OLD; return r; }
-  r.o = observe (p, f, cx, cy, cz, size);
-  if (!r.o.valid) return r;
-  if (can_split && r.o.near_) { r.kind = KIND_NEW; return r; }
+  // centre of the level-k node with hierarchical index j below a root centred at c0 (octree.cpp:251-264)
+  float x = c0[0], y = c0[1], z = c0[2];
+  for (int l = k - 1; l >= 0; --l)
+  {
+    int cc = (j >> (3 * l)) & 7;
+    x = (cc & 4) ? fadd (x, off) : fsub (x, off);
+    y = (cc & 2) ? fadd (y, off) : fsub (y, off);
+    z = (cc & 1) ? fadd (z, off) : fsub (z, off);
+    off *= 0.5f;
+  }
+  c[0] = x; c[1] = y; c[2] = z;
+}
+
+// visit one node whose state sits at smem index si.  Returns kind; rc for finished nodes.
+__device__ __forceinline__ int visit_node (const Params& p, const Frame& f, WarpSmem& S, int si, bool split_old,
+                                           const float* c, double near_thr, bool can_split, int& rc, bool& updated)
+{
+  rc = 0; updated = false;
+  if (split_old) return KIND_OLD;
+  Obs o = observe_thr (p, f, c[0], c[1], c[2], near_thr);
+  if (!o.valid) return KIND_DONE;
+  if (can_split && o.near_)
+  {
+    S.dnew[si] = o.d_new; S.uv[si] = o.u | (o.v << 16);
+    return KIND_NEW;
+  }
   float M = 0.f; int ns = 0;
-  r.rc = leaf_update_values (p, f, r.o, S.dw[si], S.rgb[si], M, ns, r.updated);
-  return r;
+  rc = leaf_update_values (p, f, o, S.dw[si], S.rgb[si], M, ns, updated);
+  return KIND_DONE;
+}
+
+// fall-through update of a node whose children were all pruned (hpp:134-137 / :179-182 then :189-214).
+// Returns false when the general path must take over (pre-existing children pruned and the node re-splits).
+__device__ __forceinline__ bool fallthrough_node (const Params& p, const Frame& f, WarpSmem& S, int si, int kind,
+                                                  const float* c, double near_thr, int& rc, bool& updated)
+{
+  Obs o; updated = false;
+  if (kind == KIND_NEW) { o.valid = true; o.near_ = true; o.d_new = S.dnew[si]; o.u = S.uv[si] & 0xFFFF; o.v = S.uv[si] >> 16; }
+  else
+  {
+    o = observe_thr (p, f, c[0], c[1], c[2], near_thr);
+    if (!o.valid) { rc = 0; return true; }
+    if (o.near_) return false;
+  }
+  float M = 0.f; int ns = 0;
+  rc = leaf_update_values (p, f, o, S.dw[si], S.rgb[si], M, ns, updated);
+  return true;
 }
 
 template <bool COLOR>
-__global__ void __launch_bounds__ (BLK_WARPS * 32) k_blocks (Params p, Frame f, Queues Q, int li, unsigned long long* __restrict__ stats)
+__global__ void __launch_bounds__ (BLK_WARPS * 32, 4) k_blocks (Params p, Frame f, Queues Q, int li,
+                                                                const int* __restrict__ blist, const int* __restrict__ bcount,
+                                                                int* __restrict__ bail, int* __restrict__ bail_count,
+                                                                unsigned long long* __restrict__ stats)
 {
-  __shared__ WarpSmem smem[BLK_WARPS];
+  __shared__ __align__ (16) WarpSmem smem[BLK_WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpSmem& S = smem[wib];
-  const int B = p.C + li;                         // block-root level = L - 3
-  int count = Q.n[li];
-  if (count > Q.cap[li]) count = Q.cap[li];
+  const int B = p.C + li;
+  const int count = *bcount;
   const int nwarps = gridDim.x * BLK_WARPS;
-  unsigned long long upd = 0, vis = 0, blocks = 0;
+  unsigned long long upd = 0, vis = 0, nblk = 0;
   const float sizeB = level_size (p, B);
-  const float off1 = sizeB * 0.25f, off2 = sizeB * 0.125f, off3 = sizeB * 0.0625f;
-  const float size1 = sizeB * 0.5f, size2 = sizeB * 0.25f, size3 = sizeB * 0.125f;
+  const float off1 = sizeB * 0.25f;
+  const double thr1 = near_threshold (sizeB * 0.5f), thr2 = near_threshold (sizeB * 0.25f);
 
   for (int wi = blockIdx.x * BLK_WARPS + wib; wi < count; wi += nwarps)
   {
-    QNode e = Q.q[li][wi];
-    NodePos nb = qnode_pos (p, B, e);
-    blocks += (lane == 0);
-    vis += (lane == 0);
-    uint32_t rm; uint32_t* rsw = split_word (p, nb, rm);
-    const bool root_old = (*rsw & rm) != 0;
-    int bslot = find_brick (p, 0, nb.x, nb.y, nb.z);
-    int kindR;
-    Obs oR; oR.valid = false;
-    if (root_old)
-    {
-      kindR = KIND_OLD;
-      if (bslot < 0) { if (lane == 0) { raise_err (p, ERR_MISSING_BRICK); Q.q[li][wi].rc = 0; } continue; }
-    }
-    else
-    {
-      oR = observe (p, f, nb.cx, nb.cy, nb.cz, nb.size);
-      if (!oR.valid) { if (lane == 0) Q.q[li][wi].rc = 0; continue; }
-      if (oR.near_)                                 // size > finest always holds at level L-3
-      {
-        kindR = KIND_NEW;
-        if (bslot < 0)
-        {
-          if (lane == 0) bslot = find_or_insert_brick (p, 0, nb.x, nb.y, nb.z);
-          bslot = __shfl_sync (0xffffffffu, bslot, 0);
-          if (bslot < 0) { if (lane == 0) Q.q[li][wi].rc = 0; continue; }
-        }
-      }
-      else
-      {
-        if (lane == 0)
-        {
-          bool updated;
-          Q.q[li][wi].rc = leaf_update (p, f, nb, oR, updated);
-          upd += updated;
-        }
-        continue;
-      }
-    }
-    // ---- stage the brick: coalesced 8-byte loads, node j3 = lane + 32 i lives at smem index 72 + j3 ----
+    const int qi = blist[wi];
+    const QNode e = Q.q[li][qi];
+    nblk += (lane == 0);
+    const int kindR = e.kind, bslot = e.child_base;
+    float c0[3] = { center1d (p, B, e.x), center1d (p, B, e.y), center1d (p, B, e.z) };
     float2* gdw = p.nodes + (size_t) bslot * BRICK_NODES;
     uchar4* grgb = COLOR ? p.rgb + (size_t) bslot * BRICK_NODES : nullptr;
     uint32_t* gsw = p.split + (size_t) bslot * BRICK_SPLIT_WORDS;
+    // ---- stage the brick with 16-byte loads ----
     __syncwarp ();
-#pragma unroll 4
-    for (int j = lane; j < BRICK_NODES; j += 32)
     {
-      S.dw[j] = gdw[j];
-      if (COLOR) S.rgb[j] = grgb[j];
+      const float4* g4 = reinterpret_cast<const float4*> (gdw);
+      float4* s4 = reinterpret_cast<float4*> (S.dw);
+#pragma unroll 5
+      for (int j = lane; j < BRICK_NODES / 2; j += 32) s4[j] = g4[j];
+      if (COLOR)
+      {
+        const uint4* gc = reinterpret_cast<const uint4*> (grgb);
+        uint4* sc = reinterpret_cast<uint4*> (S.rgb);
+#pragma unroll 5
+        for (int j = lane; j < BRICK_NODES / 4; j += 32) sc[j] = gc[j];
+      }
     }
     const uint32_t s1_old = gsw[0] & 0xFFu;
     const uint32_t s2_old0 = gsw[1], s2_old1 = gsw[2];
     __syncwarp ();
 
-    bool bail = false;
-    unsigned long long bupd = 0, bvis = 0;            // this block's counts, added on commit only
+    bool bail_f = false;
+    unsigned int bupd = 0;
     uint32_t dirty = 0;                             // bits 0-15 finest i, 16-17 level 2, 18 level 1
     // ---- level 1 (8 nodes, lanes 0..7) ----
-    NodeResult r1; r1.kind = KIND_DONE; r1.rc = 0; r1.updated = false; r1.o.valid = false;
-    float c1x = 0, c1y = 0, c1z = 0;
+    int kind1 = KIND_DONE, rc1 = 0;
     if (lane < 8)
     {
-      child_center (nb.cx, off1, (lane >> 2) & 1, c1x); child_center (nb.cy, off1, (lane >> 1) & 1, c1y); child_center (nb.cz, off1, lane & 1, c1z);
-      r1 = visit_node (p, f, S, lane, (s1_old >> lane) & 1, c1x, c1y, c1z, size1, true);
-      if (r1.updated) dirty |= 1u << 18;
-      bupd += r1.updated;
+      float c[3]; bool u_;
+      path_center (c0, off1, 1, lane, c);
+      kind1 = visit_node (p, f, S, lane, (s1_old >> lane) & 1, c, thr1, true, rc1, u_);
+      if (u_) { dirty |= 1u << 18; bupd++; }
     }
-    const uint32_t int1 = __ballot_sync (0xffffffffu, lane < 8 && r1.kind != KIND_DONE);   // interior level-1 nodes
-    const uint32_t new1 = __ballot_sync (0xffffffffu, lane < 8 && r1.kind == KIND_NEW);
-    bvis += (lane == 0) ? 8 : 0;
+    const uint32_t int1 = __ballot_sync (0xffffffffu, kind1 != KIND_DONE);
+    const uint32_t new1 = __ballot_sync (0xffffffffu, kind1 == KIND_NEW);
     // ---- level 2 (64 nodes: j2 = lane + 32 i2) ----
-    NodeResult r2[2];
+    int kind2[2], rc2[2];
     uint32_t int2[2], new2[2];
 #pragma unroll
     for (int i2 = 0; i2 < 2; ++i2)
     {
       const int j2 = lane + 32 * i2;
-      const int j1 = j2 >> 3, cc = j2 & 7;
-      r2[i2].kind = KIND_DONE; r2[i2].rc = 0; r2[i2].updated = false; r2[i2].o.valid = false;
-      const bool visited = (int1 >> j1) & 1;
-      if (visited)
+      kind2[i2] = KIND_DONE; rc2[i2] = 0;
+      if ((int1 >> (j2 >> 3)) & 1)
       {
-        float px, py, pz, cx, cy, cz;
-        child_center (nb.cx, off1, (j1 >> 2) & 1, px); child_center (nb.cy, off1, (j1 >> 1) & 1, py); child_center (nb.cz, off1, j1 & 1, pz);
-        child_center (px, off2, (cc >> 2) & 1, cx); child_center (py, off2, (cc >> 1) & 1, cy); child_center (pz, off2, cc & 1, cz);
-        const bool sold = ((i2 ? s2_old1 : s2_old0) >> lane) & 1;
-        r2[i2] = visit_node (p, f, S, 8 + j2, sold, cx, cy, cz, size2, true);
-        if (r2[i2].updated) dirty |= 1u << (16 + i2);
-        bupd += r2[i2].updated;
+        float c[3]; bool u_;
+        path_center (c0, off1, 2, j2, c);
+        kind2[i2] = visit_node (p, f, S, 8 + j2, ((i2 ? s2_old1 : s2_old0) >> lane) & 1, c, thr2, true, rc2[i2], u_);
+        if (u_) { dirty |= 1u << (16 + i2); bupd++; }
       }
-      int2[i2] = __ballot_sync (0xffffffffu, visited && r2[i2].kind != KIND_DONE);
-      new2[i2] = __ballot_sync (0xffffffffu, visited && r2[i2].kind == KIND_NEW);
+      int2[i2] = __ballot_sync (0xffffffffu, kind2[i2] != KIND_DONE);
+      new2[i2] = __ballot_sync (0xffffffffu, kind2[i2] == KIND_NEW);
     }
-    bvis += (lane == 0) ? 8 * __popc (int1) : 0;
-    bvis += (lane == 0) ? 8 * (__popc (int2[0]) + __popc (int2[1])) : 0;
     // ---- level 3 (512 finest voxels: j3 = lane + 32 i) ----
     uint32_t nonneg_mine = 0;                       // lane k (<16) keeps the ballot of iteration k
-#pragma unroll 2
+#pragma unroll 1
     for (int i = 0; i < 16; ++i)
     {
       const int j3 = lane + 32 * i;
@@ -305,15 +362,10 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32) k_blocks (Params p, Frame f, 
       int rc = 0;
       if (visited)
       {
-        const int j1 = j3 >> 6, c2 = (j3 >> 3) & 7, c3 = j3 & 7;
-        float ax, ay, az, bx, by, bz, cx, cy, cz;
-        child_center (nb.cx, off1, (j1 >> 2) & 1, ax); child_center (nb.cy, off1, (j1 >> 1) & 1, ay); child_center (nb.cz, off1, j1 & 1, az);
-        child_center (ax, off2, (c2 >> 2) & 1, bx); child_center (ay, off2, (c2 >> 1) & 1, by); child_center (az, off2, c2 & 1, bz);
-        child_center (bx, off3, (c3 >> 2) & 1, cx); child_center (by, off3, (c3 >> 1) & 1, cy); child_center (bz, off3, c3 & 1, cz);
-        NodeResult r3 = visit_node (p, f, S, 72 + j3, false, cx, cy, cz, size3, false);
-        rc = r3.rc;
-        if (r3.updated) dirty |= 1u << i;
-        bupd += r3.updated;
+        float c[3]; bool u_;
+        path_center (c0, off1, 3, j3, c);
+        visit_node (p, f, S, 72 + j3, false, c, 0.0, false, rc, u_);
+        if (u_) { dirty |= 1u << i; bupd++; }
       }
       const uint32_t nn = __ballot_sync (0xffffffffu, visited && rc >= 0);
       if (lane == i) nonneg_mine = nn;
@@ -326,42 +378,24 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32) k_blocks (Params p, Frame f, 
       const int j2 = lane + 32 * i2;
       const uint32_t nn = __shfl_sync (0xffffffffu, nonneg_mine, (lane >> 2) + 8 * i2);   // ballot of iteration j2 >> 2
       bool pruned = false;
-      if (r2[i2].kind != KIND_DONE)
+      if (kind2[i2] != KIND_DONE)
       {
-        const bool all_empty = ((nn >> (8 * (lane & 3))) & 0xFFu) == 0;
-        if (!all_empty) r2[i2].rc = 1;
+        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc2[i2] = 1;
         else
         {
           pruned = true;
-          Obs o = r2[i2].o;
-          bool ok = true;
-          if (r2[i2].kind == KIND_OLD)
-          {
-            const int j1 = j2 >> 3, cc = j2 & 7;
-            float px, py, pz, cx, cy, cz;
-            child_center (nb.cx, off1, (j1 >> 2) & 1, px); child_center (nb.cy, off1, (j1 >> 1) & 1, py); child_center (nb.cz, off1, j1 & 1, pz);
-            child_center (px, off2, (cc >> 2) & 1, cx); child_center (py, off2, (cc >> 1) & 1, cy); child_center (pz, off2, cc & 1, cz);
-            o = observe (p, f, cx, cy, cz, size2);
-            if (!o.valid) { r2[i2].rc = 0; ok = false; }
-            else if (o.near_) { bail = true; ok = false; }         // prune-then-resplit: general path
-          }
-          if (ok)
-          {
-            float M = 0.f; int ns = 0; bool updated;
-            r2[i2].rc = leaf_update_values (p, f, o, S.dw[8 + j2], S.rgb[8 + j2], M, ns, updated);
-            if (updated) dirty |= 1u << (16 + i2);
-            bupd += updated;
-          }
+          float c[3]; bool u_;
+          path_center (c0, off1, 2, j2, c);
+          if (!fallthrough_node (p, f, S, 8 + j2, kind2[i2], c, thr2, rc2[i2], u_)) bail_f = true;
+          if (u_) { dirty |= 1u << (16 + i2); bupd++; }
         }
       }
       pruned2[i2] = __ballot_sync (0xffffffffu, pruned);
-      const bool visited2 = (int1 >> (j2 >> 3)) & 1;
-      nonneg2[i2] = __ballot_sync (0xffffffffu, visited2 && r2[i2].rc >= 0);
+      nonneg2[i2] = __ballot_sync (0xffffffffu, ((int1 >> (j2 >> 3)) & 1) && rc2[i2] >= 0);
     }
-    // children of pruned level-2 nodes go back to the fresh state
-    if (pruned2[0] | pruned2[1])
+    if (pruned2[0] | pruned2[1])                    // children of pruned level-2 nodes return to the fresh state
     {
-#pragma unroll 4
+#pragma unroll 1
       for (int i = 0; i < 16; ++i)
       {
         const int j2 = (lane + 32 * i) >> 3;
@@ -375,33 +409,21 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32) k_blocks (Params p, Frame f, 
     }
     // ---- bottom-up: level 1 ----
     bool pruned1f = false;
-    if (lane < 8 && r1.kind != KIND_DONE)
+    if (lane < 8 && kind1 != KIND_DONE)
     {
       const uint32_t nn = nonneg2[lane >> 2];
-      const bool all_empty = ((nn >> (8 * (lane & 3))) & 0xFFu) == 0;
-      if (!all_empty) r1.rc = 1;
+      if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc1 = 1;
       else
       {
         pruned1f = true;
-        Obs o = r1.o;
-        bool ok = true;
-        if (r1.kind == KIND_OLD)
-        {
-          o = observe (p, f, c1x, c1y, c1z, size1);
-          if (!o.valid) { r1.rc = 0; ok = false; }
-          else if (o.near_) { bail = true; ok = false; }
-        }
-        if (ok)
-        {
-          float M = 0.f; int ns = 0; bool updated;
-          r1.rc = leaf_update_values (p, f, o, S.dw[lane], S.rgb[lane], M, ns, updated);
-          if (updated) dirty |= 1u << 18;
-          bupd += updated;
-        }
+        float c[3]; bool u_;
+        path_center (c0, off1, 1, lane, c);
+        if (!fallthrough_node (p, f, S, lane, kind1, c, thr1, rc1, u_)) bail_f = true;
+        if (u_) { dirty |= 1u << 18; bupd++; }
       }
     }
     const uint32_t pruned1 = __ballot_sync (0xffffffffu, pruned1f);
-    const uint32_t nonneg1 = __ballot_sync (0xffffffffu, lane < 8 && r1.rc >= 0);
+    const uint32_t nonneg1 = __ballot_sync (0xffffffffu, lane < 8 && rc1 >= 0);
     if (pruned1)
     {
 #pragma unroll
@@ -416,45 +438,28 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32) k_blocks (Params p, Frame f, 
         }
       }
     }
-    // ---- root ----
+    // ---- root (its state lives in the parent tier / root arrays) ----
     int rcR = 1;
-    bool prunedR = false, root_updated = false;
-    float2 rdw = make_float2 (0.f, 0.f); uchar4 rrgb = make_uchar4 (0, 0, 0, 0);
-    if ((nonneg1 & 0xFFu) == 0)
+    const bool prunedR = (nonneg1 & 0xFFu) == 0;
+    bool root_updated = false;
+    NodePos nb;
+    nb.level = B; nb.x = e.x; nb.y = e.y; nb.z = e.z; nb.cx = c0[0]; nb.cy = c0[1]; nb.cz = c0[2]; nb.size = sizeB; nb.slot = e.slot; nb.idx = e.idx;
+    Obs oR; oR.valid = false;
+    if (prunedR)
     {
-      prunedR = true;
-      Obs o = oR;
-      bool ok = true;
-      if (kindR == KIND_OLD)
-      {
-        o = observe (p, f, nb.cx, nb.cy, nb.cz, nb.size);
-        if (!o.valid) { rcR = 0; ok = false; }
-        else if (o.near_) { bail = true; ok = false; }
-      }
-      if (ok)
-      {
-        rdw = *node_dw (p, nb);
-        if (COLOR) rrgb = nb.slot < 0 ? p.root_rgb[nb.idx] : p.rgb[(size_t) nb.slot * BRICK_NODES + nb.idx];
-        float M = 0.f; int ns = 0;
-        rcR = leaf_update_values (p, f, o, rdw, rrgb, M, ns, root_updated);
-      }
+      oR = observe (p, f, c0[0], c0[1], c0[2], sizeB);
+      if (kindR == KIND_OLD && oR.valid && oR.near_) bail_f = true;
     }
-    bail = __any_sync (0xffffffffu, bail);
-    if (bail)
+    if (__any_sync (0xffffffffu, bail_f))
     {
-      // nothing has been committed: redo this block root with the general depth-first routine
-      if (lane == 0)
-      {
-        Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
-        Q.q[li][wi].rc = update_voxel_dfs (p, f, nb, cnt);
-        upd += cnt.n_updates;
-        vis += cnt.n_visits - 1;          // the root visit was counted above
-      }
+      // nothing has been committed: hand this block root to the general depth-first routine (k_bail)
+      if (lane == 0) bail[atomicAdd (bail_count, 1)] = qi;
       __syncwarp ();
       continue;
     }
-    upd += bupd; vis += bvis;
     // ---- commit ----
+    upd += bupd;
+    vis += (lane == 0) ? (8 + 8 * (__popc (int1) + __popc (int2[0]) + __popc (int2[1]))) : 0;
     __syncwarp ();
 #pragma unroll 4
     for (int i = 0; i < 16; ++i)
@@ -471,25 +476,23 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32) k_blocks (Params p, Frame f, 
         if (COLOR) grgb[8 + lane + 32 * i2] = S.rgb[8 + lane + 32 * i2];
       }
     if ((dirty >> 18) & 1) { gdw[lane] = S.dw[lane]; if (COLOR) grgb[lane] = S.rgb[lane]; }
-    // level-1 nodes reset by a root prune
     if (prunedR && lane < 8) { gdw[lane] = make_float2 (-1.f, 0.f); if (COLOR) grgb[lane] = make_uchar4 (0, 0, 0, 0); }
     if (lane == 0)
     {
-      const uint32_t s1_new = ((s1_old | (new1 & 0xFFu)) & ~(pruned1 & 0xFFu)) & 0xFFu;
+      const uint32_t s1_new = ((s1_old | (new1 & 0xFFu)) & ~(pruned1 & 0xFFu)) & 0xFFu;   // all zero when the root is pruned
       const uint32_t s2_new0 = (s2_old0 | new2[0]) & ~pruned2[0];
       const uint32_t s2_new1 = (s2_old1 | new2[1]) & ~pruned2[1];
-      if (s1_new != s1_old) gsw[0] = s1_new;         // (all zero when the root is pruned: every child is a leaf then)
+      if (s1_new != s1_old) gsw[0] = s1_new;
       if (s2_new0 != s2_old0) gsw[1] = s2_new0;
       if (s2_new1 != s2_old1) gsw[2] = s2_new1;
-      if (kindR == KIND_NEW && !prunedR) atomicOr (rsw, rm);
-      if (kindR == KIND_OLD && prunedR) atomicAnd (rsw, ~rm);
-      if (root_updated)
+      if (prunedR)
       {
-        *node_dw (p, nb) = rdw;
-        if (COLOR) { if (nb.slot < 0) p.root_rgb[nb.idx] = rrgb; else p.rgb[(size_t) nb.slot * BRICK_NODES + nb.idx] = rrgb; }
-        upd += 1;
+        uint32_t rm; uint32_t* rsw = split_word (p, nb, rm);
+        atomicAnd (rsw, ~rm);                      // (k_upper_down set the bit for a root split this frame)
+        rcR = 0;
+        if (oR.valid) { rcR = leaf_update (p, f, nb, oR, root_updated); upd += root_updated; }
       }
-      Q.q[li][wi].rc = rcR;
+      Q.q[li][qi].rc = rcR;
     }
     __syncwarp ();
   }
@@ -499,13 +502,30 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32) k_blocks (Params p, Frame f, 
   {
     upd += __shfl_down_sync (0xffffffffu, upd, o);
     vis += __shfl_down_sync (0xffffffffu, vis, o);
-    blocks += __shfl_down_sync (0xffffffffu, blocks, o);
   }
   if (lane == 0)
   {
     if (upd) atomicAdd (&stats[0], upd);
     if (vis) atomicAdd (&stats[1], vis);
-    if (blocks) atomicAdd (&stats[2], blocks);
+    if (nblk) atomicAdd (&stats[2], nblk);
+  }
+}
+
+// the rare non-separable case: redo the block root depth-first on the (untouched) global state
+__global__ void k_bail (Params p, Frame f, Queues Q, int li, const int* __restrict__ bail, const int* __restrict__ bail_count,
+                        unsigned long long* __restrict__ stats)
+{
+  int count = *bail_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+  {
+    int qi = bail[i];
+    QNode e = Q.q[li][qi];
+    NodePos n = qnode_pos (p, p.C + li, e);
+    if (e.kind == KIND_NEW) { uint32_t m; uint32_t* sw = split_word (p, n, m); atomicAnd (sw, ~m); }   // undo the speculative split
+    Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
+    Q.q[li][qi].rc = update_voxel_dfs (p, f, n, cnt);
+    atomicAdd (&stats[0], (unsigned long long) cnt.n_updates);
+    atomicAdd (&stats[1], (unsigned long long) (cnt.n_visits - 1));
   }
 }
 

@@ -284,6 +284,7 @@ struct b200tsdf
   bool is_empty = true;          // TSDFVolumeOctree::is_empty_ (cpp:205, hpp:101)
   // fast-path work queues (levels C .. L-3)
   Queues Q{}; int q_levels = 0; QNode* q_mem = nullptr; size_t q_mem_cap = 0;
+  int* d_blist = nullptr; int* d_bail = nullptr; size_t blist_cap = 0;
   bool fast_path = false; int force_general = 0;
   // measurement
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
@@ -385,7 +386,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
   free_volume (h);
   cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled);
-  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem);
+  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
   if (h->ev_k0) cudaEventDestroy (h->ev_k0); if (h->ev_k1) cudaEventDestroy (h->ev_k1);
@@ -474,6 +475,14 @@ int b200tsdf_reset (b200tsdf_t* h)
     for (int i = 0; i < MAX_QLEVELS; ++i) { h->Q.q[i] = nullptr; h->Q.cap[i] = 0; }
     for (int i = 0; i < h->q_levels; ++i) { h->Q.q[i] = h->q_mem + off; h->Q.cap[i] = (int) caps[i]; off += caps[i]; }
     h->Q.n = h->d_count;
+    size_t bl = h->q_levels ? caps[h->q_levels - 1] : 0;
+    if (bl > h->blist_cap)
+    {
+      cudaFree (h->d_blist); cudaFree (h->d_bail); h->d_blist = h->d_bail = nullptr; h->blist_cap = 0;
+      CK (cudaMalloc (&h->d_blist, bl * sizeof (int)));
+      CK (cudaMalloc (&h->d_bail, bl * sizeof (int)));
+      h->blist_cap = bl;
+    }
   }
   Params& p = h->p;
   {
@@ -530,12 +539,14 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   if (h->fast_path)
   {
     const int nl = h->q_levels;
-    for (int li = 0; li < nl - 1; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
+    int* d_bcount = h->d_count + 9; int* d_bailcount = h->d_count + 10;
+    for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
     CK (cudaEventRecord (h->kring[kr][0], s));
-    if (p.color) k_blocks<true><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_stats);
-    else k_blocks<false><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_stats);
+    if (p.color) k_blocks<true><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
+    else k_blocks<false><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
     CK (cudaEventRecord (h->kring[kr][1], s));
-    h->launches++;
+    k_bail<<<8, 64, 0, s>>> (p, f, h->Q, nl - 1, h->d_bail, d_bailcount, h->d_stats);
+    h->launches += 2;
     for (int li = nl - 2; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
   }
   else

@@ -44,6 +44,8 @@ inline const char* derive_params (const b200tsdf_config& c, Params& p, size_t& p
   p.min_sensor = c.min_sensor_dist; p.max_sensor = c.max_sensor_dist;
   p.rc_thresh = 0.99 * c.max_dist_pos / c.max_dist_neg;
   p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy; p.width = c.image_width; p.height = c.image_height;
+  p.fx_f = (float) c.fx; p.fy_f = (float) c.fy; p.cx_f = (float) c.cx; p.cy_f = (float) c.cy;
+  p.fast_proj = (c.image_width < 8192 && c.image_height < 8192 && std::fabs (c.cx) < 1e4 && std::fabs (c.cy) < 1e4) ? 1 : 0;
   p.color = c.integrate_color != 0; p.track_var = c.track_variance != 0;
   p.shard_rank = c.shard_rank; p.shard_count = c.shard_count;
   p.pool_mask = (uint32_t) (pool - 1);

@@ -132,6 +132,8 @@ struct Params
   float max_dist_pos, max_dist_neg, max_weight, min_sensor, max_sensor;
   double rc_thresh;           // 0.99 * max_dist_pos_ / max_dist_neg_ (hpp:211)
   double fx, fy, cx, cy;
+  float fx_f, fy_f, cx_f, cy_f;   // float-rounded intrinsics for the guarded fast projection (see project_pixel)
+  int fast_proj;                  // 1 when the guard's error bound holds (image < 8192 px)
   int width, height;
   int color, track_var;
   // sharding: this device owns coarse cells with cell_hash % shard_count == shard_rank
@@ -424,24 +426,49 @@ struct Obs
   float d_new;      // pt.z - v_g.z, unclamped
 };
 
-B2_HD Obs observe (const Params& p, const Frame& f, float cx, float cy, float cz, float size)
+// reprojectPoint (tsdf_volume_octree.cpp:611-617): u = (int)(x*fx/z + cx) in DOUBLE, truncation toward
+// zero.  The double divide is ~10x the cost of everything else in a node visit, so a float estimate
+// is tried first and accepted only where it provably truncates to the same integer: its error is
+// below 2^-24 * (3.01|x fx/z| + |cx| + |a|) < 4e-3 for |a| < 3e4, and the estimate must sit at least
+// 1e-2 away from an integer (and above 0).  Otherwise the reference's double expression is evaluated.
+B2_HD int project1 (const Params& p, float x, float z, double fd, double cd, float ff, float cf)
+{
+  if (p.fast_proj)
+  {
+    float a = fadd (fdiv (fmul (x, ff), z), cf);
+    float fr = a - floorf (a);
+    if (a > 0.01f && a < 30000.f && fr > 0.01f && fr < 0.99f) return (int) a;
+  }
+  return to_int_x86 (dadd (ddiv (dmul ((double) x, fd), (double) z), cd));
+}
+
+// |d_new| < 3*getMaxSize()/4. (hpp:161): the right-hand side depends on the node size only
+B2_HD double near_threshold (float size)
+{
+  float max_size = (float) dmul (1.7320508075688772, (double) size);          // getMaxSize(), octree.cpp:68-72
+  return ddiv ((double) fmul (3.f, max_size), 4.0);
+}
+
+B2_HD Obs observe_thr (const Params& p, const Frame& f, float cx, float cy, float cz, double near_thr)
 {
   Obs o; o.valid = false; o.near_ = false; o.u = o.v = 0; o.d_new = 0.f;
   float vg[3];
   pcl_transform_point_f (f.tinv, cx, cy, cz, vg);                              // hpp:145
   if (vg[2] < p.min_sensor || vg[2] > p.max_sensor) return o;                  // hpp:146
-  // reprojectPoint, tsdf_volume_octree.cpp:611-617 (double math, truncation toward zero)
-  int u = to_int_x86 (dadd (ddiv (dmul ((double) vg[0], p.fx), (double) vg[2]), p.cx));
-  int v = to_int_x86 (dadd (ddiv (dmul ((double) vg[1], p.fy), (double) vg[2]), p.cy));
-  if (!(vg[2] > 0 && u >= 0 && u < p.width && v >= 0 && v < p.height)) return o;
+  if (!(vg[2] > 0)) return o;                                                  // cpp:616
+  int u = project1 (p, vg[0], vg[2], p.fx, p.cx, p.fx_f, p.cx_f);
+  int v = project1 (p, vg[1], vg[2], p.fy, p.cy, p.fy_f, p.cy_f);
+  if (!(u >= 0 && u < p.width && v >= 0 && v < p.height)) return o;
   float z = frame_xyz (f, u, v)[2];
   if (is_nan (z)) return o;                                                    // hpp:152
   o.valid = true; o.u = u; o.v = v;
   o.d_new = fsub (z, vg[2]);                                                   // hpp:159
-  float max_size = (float) dmul (1.7320508075688772, (double) size);          // getMaxSize(), octree.cpp:68-72
-  o.near_ = (double) fabsf (o.d_new) < ddiv ((double) fmul (3.f, max_size), 4.0);
+  o.near_ = (double) fabsf (o.d_new) < near_thr;
   return o;
 }
+
+B2_HD Obs observe (const Params& p, const Frame& f, float cx, float cy, float cz, float size)
+{ return observe_thr (p, f, cx, cy, cz, near_threshold (size)); }
 
 // truncation + addObservation + return code (hpp:189-214, octree.cpp:152-163, :328-337) on VALUES:
 // dw / c / M / ns are the node's state (in registers, shared memory or wherever the caller staged
