@@ -734,17 +734,20 @@ B2_HD bool query_point (const Params& p, const float* pt, int mode, float* val, 
         Leaf lf = find_leaf (p, fx_, fy_, fz_);
         if (!lf.found) return false;
         float vx = mode ? fx_ : lf.n.cx, vy = mode ? fy_ : lf.n.cy, vz = mode ? fz_ : lf.n.cz;
-        float ax = fsub (c, fabsf (fsub (pt[0], vx))), ay = fsub (c, fabsf (fsub (pt[1], vy))), az = fsub (c, fabsf (fsub (pt[2], vz)));
-        float sx = (float) -sgn (fsub (pt[0], vx)), sy = (float) -sgn (fsub (pt[1], vy)), sz = (float) -sgn (fsub (pt[2], vz));
-        fv = fadd (fv, fmul (fmul (fmul (ax, ay), az), lf.d));
-        g0 = fadd (g0, fmul (fmul (fmul (sx, ay), az), lf.d));
-        g1 = fadd (g1, fmul (fmul (fmul (ax, sy), az), lf.d));
-        g2 = fadd (g2, fmul (fmul (fmul (ax, ay), sz), lf.d));
-        float bx = fsub (c, fabsf (fsub (pt[0], fx_))), by = fsub (c, fabsf (fsub (pt[1], fy_))), bz = fsub (c, fabsf (fsub (pt[2], fz_)));
+        // unqualified fabs() in the reference is the C double version: the factors and products are
+        // DOUBLE, only the `+=` rounds to float (cpp:668, 694-696, 716-718; see oracle/tsdf_oracle.cpp)
+        const double dc = (double) c, dd = (double) lf.d;
+        double ax = dadd (dc, -fabs ((double) fsub (pt[0], vx))), ay = dadd (dc, -fabs ((double) fsub (pt[1], vy))), az = dadd (dc, -fabs ((double) fsub (pt[2], vz)));
+        double sx = (double) -sgn (fsub (pt[0], vx)), sy = (double) -sgn (fsub (pt[1], vy)), sz = (double) -sgn (fsub (pt[2], vz));
+        fv = (float) dadd ((double) fv, dmul (dmul (dmul (ax, ay), az), dd));
+        g0 = (float) dadd ((double) g0, dmul (dmul (dmul (sx, ay), az), dd));
+        g1 = (float) dadd ((double) g1, dmul (dmul (dmul (ax, sy), az), dd));
+        g2 = (float) dadd ((double) g2, dmul (dmul (dmul (ax, ay), sz), dd));
+        double bx = dadd (dc, -fabs ((double) fsub (pt[0], fx_))), by = dadd (dc, -fabs ((double) fsub (pt[1], fy_))), bz = dadd (dc, -fabs ((double) fsub (pt[2], fz_)));
         int tx = sgn (fsub (pt[0], fx_)), ty = sgn (fsub (pt[1], fy_)), tz = sgn (fsub (pt[2], fz_));
-        h01 = fadd (h01, fmul (fmul ((float) (tx * ty), bz), lf.d));
-        h02 = fadd (h02, fmul (fmul (fmul ((float) tx, by), (float) tz), lf.d));
-        h12 = fadd (h12, fmul (fmul (fmul (bx, (float) ty), (float) tz), lf.d));
+        h01 = (float) dadd ((double) h01, dmul (dmul ((double) (tx * ty), bz), dd));
+        h02 = (float) dadd ((double) h02, dmul (dmul (dmul ((double) tx, by), (double) tz), dd));
+        h12 = (float) dadd ((double) h12, dmul (dmul (dmul (bx, (double) ty), (double) tz), dd));
       }
   float c3 = fmul (fmul (c, c), c);
   if (val) *val = fdiv (fv, c3);
@@ -835,7 +838,8 @@ B2_HD void render_pixel (const Params& p, const RenderParams& r, int x, int y, f
     float tcurr = t, tprev = fsub (t, step);
     last_d = interpolate_trilinearly (p, fadd (org[0], fmul (tprev, du[0])), fadd (org[1], fmul (tprev, du[1])), fadd (org[2], fmul (tprev, du[2])), &has_data);
     d = interpolate_trilinearly (p, fadd (org[0], fmul (tcurr, du[0])), fadd (org[1], fmul (tcurr, du[1])), fadd (org[2], fmul (tcurr, du[2])), &has_data);
-    float t_star = fadd (t, fmul (step, fadd (-1.f, fabsf (fdiv (last_d, fsub (last_d, d))))));
+    // cpp:389 — fabs() is the C double version: the right-hand side is evaluated in double, rounded once
+    float t_star = (float) dadd ((double) t, dmul ((double) step, dadd (-1.0, fabs ((double) fdiv (last_d, fsub (last_d, d))))));
     P[0] = fadd (org[0], fmul (t_star, du[0])); P[1] = fadd (org[1], fmul (t_star, du[1])); P[2] = fadd (org[2], fmul (t_star, du[2]));
     have_point = true;
     Leaf lf = find_leaf (p, P[0], P[1], P[2]);

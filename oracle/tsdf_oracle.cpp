@@ -515,17 +515,22 @@ int orc_query (const orc_volume* v, const float* xyz, int n, int what, int mode,
     {
       const Node* vox = nb[k];
       // getFxn/getGradient measure to the leaf's own centre (cpp:667, 693); getHessian and the
-      // combined variants use the finest-voxel centres (cpp:715, 744, 777)
+      // combined variants use the finest-voxel centres (cpp:715, 744, 777).
+      // The reference calls unqualified fabs() on floats: with <cmath> alone that is the C
+      // double fabs(double), so each (c - fabs(..)) factor and the whole product are DOUBLE and
+      // only the `+=` rounds back to float (verified against the verbatim build, oracle/_ref).
       float lx = vox->cx, ly = vox->cy, lz = vox->cz;
       float fx_ = ctrs[k][0], fy_ = ctrs[k][1], fz_ = ctrs[k][2];
       float vx = mode ? fx_ : lx, vy = mode ? fy_ : ly, vz = mode ? fz_ : lz;
-      fv   += (c - std::fabs (p[0] - vx)) * (c - std::fabs (p[1] - vy)) * (c - std::fabs (p[2] - vz)) * vox->d;
-      g[0] += -sgn (p[0] - vx) * (c - std::fabs (p[1] - vy)) * (c - std::fabs (p[2] - vz)) * vox->d;
-      g[1] += (c - std::fabs (p[0] - vx)) * -sgn (p[1] - vy) * (c - std::fabs (p[2] - vz)) * vox->d;
-      g[2] += (c - std::fabs (p[0] - vx)) * (c - std::fabs (p[1] - vy)) * -sgn (p[2] - vz) * vox->d;
-      h01 += sgn (p[0] - fx_) * sgn (p[1] - fy_) * (c - std::fabs (p[2] - fz_)) * vox->d;
-      h02 += sgn (p[0] - fx_) * (c - std::fabs (p[1] - fy_)) * sgn (p[2] - fz_) * vox->d;
-      h12 += (c - std::fabs (p[0] - fx_)) * sgn (p[1] - fy_) * sgn (p[2] - fz_) * vox->d;
+      double ax = c - fabs ((double) (p[0] - vx)), ay = c - fabs ((double) (p[1] - vy)), az = c - fabs ((double) (p[2] - vz));
+      double bx = c - fabs ((double) (p[0] - fx_)), by = c - fabs ((double) (p[1] - fy_)), bz = c - fabs ((double) (p[2] - fz_));
+      fv   += ax * ay * az * vox->d;
+      g[0] += -sgn (p[0] - vx) * ay * az * vox->d;
+      g[1] += ax * -sgn (p[1] - vy) * az * vox->d;
+      g[2] += ax * ay * -sgn (p[2] - vz) * vox->d;
+      h01 += sgn (p[0] - fx_) * sgn (p[1] - fy_) * bz * vox->d;
+      h02 += sgn (p[0] - fx_) * by * sgn (p[2] - fz_) * vox->d;
+      h12 += bx * sgn (p[1] - fy_) * sgn (p[2] - fz_) * vox->d;
     }
     float c3 = (c * c * c);
     if ((what & 1) && val) val[i] = fv / c3;
@@ -629,7 +634,8 @@ int orc_render (const orc_volume* v, const double* pose, int downsampleBy, void*
     last_d = v->interpolate_trilinearly (org[0] + tprev * du[0], org[1] + tprev * du[1], org[2] + tprev * du[2], &has_data);
     d = v->interpolate_trilinearly (org[0] + tcurr * du[0], org[1] + tcurr * du[1], org[2] + tcurr * du[2], &has_data);
     // cpp:385-388 sets NaN but cpp:389-390 overwrites it (no `continue`)
-    float t_star = t + step * (-1 + std::fabs (last_d / (last_d - d)));
+    // fabs() is the C double version here too: the whole right-hand side is evaluated in double
+    float t_star = t + step * (-1 + fabs ((double) (last_d / (last_d - d))));
     float pt[3] = { org[0] + t_star * du[0], org[1] + t_star * du[1], org[2] + t_star * du[2] };
     P[0] = pt[0]; P[1] = pt[1]; P[2] = pt[2];
     int32_t ni = v->containing (pt[0], pt[1], pt[2]);
