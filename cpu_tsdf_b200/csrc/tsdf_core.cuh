@@ -735,7 +735,7 @@ B2_HD bool query_point (const Params& p, const float* pt, int mode, float* val, 
         if (!lf.found) return false;
         float vx = mode ? fx_ : lf.n.cx, vy = mode ? fy_ : lf.n.cy, vz = mode ? fz_ : lf.n.cz;
         // unqualified fabs() in the reference is the C double version: the factors and products are
-        // DOUBLE, only the `+=` rounds to float (cpp:668, 694-696, 716-718; see oracle/tsdf_oracle.cpp)
+        // DOUBLE, only the `+=` rounds to float (cpp:668, 694-696, 716-718; DESIGN.md "Arithmetic conventions")
         const double dc = (double) c, dd = (double) lf.d;
         double ax = dadd (dc, -fabs ((double) fsub (pt[0], vx))), ay = dadd (dc, -fabs ((double) fsub (pt[1], vy))), az = dadd (dc, -fabs ((double) fsub (pt[2], vz)));
         double sx = (double) -sgn (fsub (pt[0], vx)), sy = (double) -sgn (fsub (pt[1], vy)), sz = (double) -sgn (fsub (pt[2], vz));
