@@ -63,7 +63,7 @@ class Profile(C.Structure):
 EXPORTS = [
     "b200tsdf_default_config", "b200tsdf_create", "b200tsdf_destroy", "b200tsdf_last_error",
     "b200tsdf_set_config", "b200tsdf_get_config", "b200tsdf_reset", "b200tsdf_integrate",
-    "b200tsdf_integrate_device", "b200tsdf_sync", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
+    "b200tsdf_integrate_device", "b200tsdf_integrate_async", "b200tsdf_sync", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
     "b200tsdf_free", "b200tsdf_save", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
     "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_frustum_cull",
     "b200tsdf_profile_begin", "b200tsdf_profile_end",
@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
     lib.b200tsdf_reset.argtypes = [vp]
     lib.b200tsdf_integrate.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_integrate_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.b200tsdf_integrate_async.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_sync.argtypes = [vp]
     lib.b200tsdf_query.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.b200tsdf_render.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, vp]
@@ -236,6 +237,13 @@ class TSDFVolumeOctree:
         H, W, nf = cloud.shape
         pose = _pose(trans)
         self._check(self._lib.b200tsdf_integrate(self._h, _ptr(cloud), nf * 4, 0, 16 if nf >= 5 else -1, W, H, _ptr(pose)))
+        return True
+
+    def integrateCloudAsync(self, host_ptr: int, height: int, width: int, stride: int, trans, rgba_off: int = -1) -> bool:
+        """Streaming integrateCloud from a (pinned) host buffer that the caller keeps alive until
+        sync(): returns once the copy and the kernels are enqueued (b200tsdf_integrate_async)."""
+        pose = _pose(trans)
+        self._check(self._lib.b200tsdf_integrate_async(self._h, C.c_void_p(host_ptr), stride, 0, rgba_off, width, height, _ptr(pose)))
         return True
 
     def integrateCloudDevice(self, d_ptr: int, height: int, width: int, stride: int, trans, rgba_off: int = -1) -> bool:

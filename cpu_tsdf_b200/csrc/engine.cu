@@ -576,8 +576,8 @@ int b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t strid
   return integrate_on_device (h, (const unsigned char*) d_points, stride, xyz_off, rgba_off, width, height, pose);
 }
 
-int b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
-                        int width, int height, const double* pose)
+static int integrate_host (b200tsdf* h, const void* points, size_t stride, int xyz_off, int rgba_off,
+                           int width, int height, const double* pose, bool wait_copy)
 {
   if (!h || !points || !pose) return B200TSDF_EINVAL;
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
@@ -602,9 +602,17 @@ int b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int xy
   if (rc) return rc;
   CK (cudaEventRecord (h->ev_consumed[b], h->stream));
   h->frame_no++;
-  CK (cudaEventSynchronize (h->ev_copied[b]));       // the caller may reuse its buffer now
+  if (wait_copy) CK (cudaEventSynchronize (h->ev_copied[b]));       // the caller may reuse its buffer now
   return B200TSDF_OK;
 }
+
+int b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
+                        int width, int height, const double* pose)
+{ return integrate_host (h, points, stride, xyz_off, rgba_off, width, height, pose, true); }
+
+int b200tsdf_integrate_async (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
+                              int width, int height, const double* pose)
+{ return integrate_host (h, points, stride, xyz_off, rgba_off, width, height, pose, false); }
 
 int b200tsdf_sync (b200tsdf_t* h)
 {

@@ -80,6 +80,11 @@ int  b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int x
  * handle's stream; call b200tsdf_sync before reading results on the host) */
 int  b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t stride, int xyz_off, int rgba_off,
                                 int width, int height, const double* pose_c2w);
+/* streaming variant of b200tsdf_integrate for producers that keep their (pinned) frame buffers alive:
+ * returns as soon as the copy and the kernels are enqueued.  `points` must stay valid and unmodified
+ * until b200tsdf_sync() or until two further frames have been submitted on this handle. */
+int  b200tsdf_integrate_async (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
+                               int width, int height, const double* pose_c2w);
 int  b200tsdf_sync (b200tsdf_t* h);
 
 /* getFxn / getGradient / getHessian (cpp:655-725) with mode 0, or the combined

@@ -207,3 +207,31 @@ def test_errors_are_reported_not_thrown():
     with pytest.raises(pkg.B200Error):
         small.integrateCloud(synth.make_frame(synth.S1, pose, CAM), None, pose)
         small.sync()
+
+
+def test_sharded_volumes_union_is_the_whole_volume():
+    # shard by coarse cell; here both shards live on one GPU (two handles), the multi-GPU
+    # launch in bench.py only changes the device ordinal
+    from tests.shard_worker import cell_owner
+    o = OracleVolume(**CFG_256); o.reset()
+    shards = []
+    for r in range(2):
+        v = pkg.TSDFVolumeOctree(device=0, pool_log2=16, shard_rank=r, shard_count=2)
+        v.setResolution(256, 256, 256); v.setCameraIntrinsics(525.0, 525.0, CAM.cx, CAM.cy); v.reset()
+        shards.append(v)
+    total = 0
+    for pose, cloud in frames(synth.S1, 3, stride=11, noise_seed=21):
+        o.integrate(cloud, pose); total += o.stats().n_add_observation
+        for v in shards:
+            v.integrateCloud(cloud, None, pose)
+            total -= v.stats().n_updates
+    assert total == 0                                     # every voxel update happened on exactly one shard
+    ref = o.dump_nodes()
+    C = o.levels()[0]
+    owner = np.array([cell_owner(*c, 2) for c in (ref["keys"][:, 1:] >> (ref["keys"][:, 0:1] - C))])
+    for r, v in enumerate(shards):
+        d = v.download_nodes()
+        own = np.array([cell_owner(*c, 2) for c in (d["keys"][:, 1:] >> (d["keys"][:, 0:1] - C))]) == r
+        assert np.array_equal(d["keys"][own], ref["keys"][owner == r])
+        assert np.array_equal(d["dw"][own].view(np.uint32), ref["dw"][owner == r].view(np.uint32))
+        assert (d["dw"][~own] == [-1, 0]).all() and not d["split"][~own].any()
