@@ -295,7 +295,9 @@ def main():
                 "bytes_per_launch": b_alg_local / max(1, prof.kernel_launches),
                 "us_per_launch": 1e3 * prof.ms_kernel / max(1, prof.kernel_launches),
                 "updates_per_frame": prof.n_updates / max(1, prof.n_frames),
-                "blocks_last_frame": int(vol.stats().n_block_visits), "bricks_allocated": int(vol.stats().n_bricks)}
+                "blocks_last_frame": int(vol.stats().n_block_visits), "bricks_allocated": int(vol.stats().n_bricks),
+                "general_path_last_frame": {"block_bails": int(vol.stats().n_bail), "upper_slow_folds": int(vol.stats().reserved),
+                                            "upper_slow_visits": int(vol.stats().n_slow_visits)}}
 
     if rank == 0:
         cpu = None

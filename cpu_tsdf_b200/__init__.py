@@ -49,6 +49,7 @@ class Stats(C.Structure):
         ("n_bricks", C.c_int64), ("n_block_visits", C.c_int64), ("pool_capacity", C.c_int64),
         ("coarse_level", C.c_int32), ("finest_level", C.c_int32), ("tiers", C.c_int32), ("reserved", C.c_int32),
         ("ms_last_integrate", C.c_double), ("ms_last_kernel", C.c_double),
+        ("n_bail", C.c_int64), ("n_slow_visits", C.c_int64),
     ]
 
 

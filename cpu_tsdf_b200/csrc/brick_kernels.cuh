@@ -206,6 +206,248 @@ __global__ void k_upper_up (Params p, Frame f, Queues Q, int li, unsigned long l
   warp_add_stats (stats, upd, vis);
 }
 
+// ---- 1b/3b. fused upper sweeps: one CTA per culled coarse cell ---------------------------------------------
+// When the block-root level is at most three levels below the coarse depth (2048^3/10 m, 512^3/3 m: C..C+3),
+// the whole upper pyramid of one coarse cell (1 + 8 + 64 nodes + up to 512 block roots) fits in shared memory.
+// k_cell_down walks it level by level inside one CTA (a __syncthreads between levels instead of a kernel
+// launch) and k_cell_up folds it back.  Same per-node rules as k_upper_down / k_upper_up.
+constexpr int CELL_THREADS = 128;
+struct CellRecord { int n[4]; };                 // entries per relative level 0..3 for this cell
+
+__device__ __forceinline__ int upper_visit (const Params& p, const Frame& f, int level, QNode& e, NodePos& n, int& cs,
+                                            unsigned long long& upd)
+{
+  // returns 0 = finished, 1 = interior (children to be visited); e.kind / e.rc are set
+  n = qnode_pos (p, level, e);
+  cs = -1;
+  uint32_t m; uint32_t* sw = split_word (p, n, m);
+  if (*sw & m)                                                      // hpp:122
+  {
+    cs = children_slot (p, n, false);
+    if (cs < 0) { raise_err (p, ERR_MISSING_BRICK); e.kind = KIND_DONE; e.rc = 0; return 0; }
+    e.kind = KIND_OLD;
+    return 1;
+  }
+  Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
+  if (!o.valid) { e.kind = KIND_DONE; e.rc = 0; return 0; }
+  if (o.near_ && n.size > p.finest_size)                             // hpp:161-166
+  {
+    cs = children_slot (p, n, true);
+    if (cs < 0) { e.kind = KIND_DONE; e.rc = 0; return 0; }
+    e.kind = KIND_NEW;
+    atomicOr (sw, m);                                                // split (): children are fresh by invariant
+    return 1;
+  }
+  bool updated;
+  e.rc = leaf_update (p, f, n, o, updated);
+  e.kind = KIND_DONE;
+  upd += updated;
+  return 0;
+}
+
+// fold the children's return codes into an interior node (hpp:131-142 / :176-188 + fall-through)
+__device__ unsigned long long* g_diag;   // [0] slow folds in the upper sweeps, [1] visits inside them (diagnostics)
+__device__ __noinline__ int upper_fold_slow (const Params& p, const Frame& f, const NodePos& n, unsigned long long& upd, unsigned long long& vis)
+{
+  Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
+  int rc = update_voxel_dfs (p, f, n, cnt);
+  upd += cnt.n_updates; vis += cnt.n_visits - 1;
+  if (g_diag) { atomicAdd (&g_diag[0], 1ull); atomicAdd (&g_diag[1], (unsigned long long) cnt.n_visits); }
+  return rc;
+}
+// leaf visit (hpp:143-218) of a node whose pre-existing children were just pruned, by one WARP: if the node
+// re-splits, its eight fresh children are visited by lanes 0..7 in parallel (their subtrees are disjoint).
+// All 32 lanes must call it with the same node.  Returns the node's return code in every lane.
+__device__ __noinline__ int leaf_visit_warp8 (const Params& p, const Frame& f, const NodePos& n, unsigned long long& upd, unsigned long long& vis)
+{
+  const int lane = threadIdx.x & 31;
+  Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
+  if (!o.valid) return 0;
+  Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
+  if (o.near_ && n.size > p.finest_size)
+  {
+    uint32_t m; uint32_t* sw = split_word (p, n, m);
+    int cs = -1;
+    if (lane == 0) cs = children_slot (p, n, true);
+    cs = __shfl_sync (0xffffffffu, cs, 0);
+    if (cs >= 0)
+    {
+      if (lane == 0) atomicOr (sw, m);
+      __syncwarp ();
+      int rc = -1;
+      NodePos ch;
+      if (lane < 8)
+      {
+        ch = make_child (p, n, lane, cs);
+        Obs oc = observe (p, f, ch.cx, ch.cy, ch.cz, ch.size);
+        rc = visit_fresh_leaf (p, f, ch, oc, cnt);
+      }
+      const unsigned nonneg = __ballot_sync (0xffffffffu, lane < 8 && rc >= 0);
+      upd += cnt.n_updates; vis += cnt.n_visits;
+      if (nonneg) return 1;
+      if (lane == 0) atomicAnd (sw, ~m);
+      if (lane < 8) reset_node (p, ch);
+      __syncwarp ();
+    }
+  }
+  int rc = 0;
+  if (lane == 0) { bool updated; rc = leaf_update (p, f, n, o, updated); upd += updated; }
+  return __shfl_sync (0xffffffffu, rc, 0);
+}
+
+constexpr int RC_DEFERRED = 2;   // upper_fold: the node needs the general leaf visit (caller decides how)
+__device__ __forceinline__ int upper_fold (const Params& p, const Frame& f, int level, const QNode& e, bool all_empty,
+                                           unsigned long long& upd, unsigned long long& vis, bool defer_slow = false)
+{
+  if (!all_empty) return 1;                                          // hpp:140 / :185
+  NodePos n = qnode_pos (p, level, e);
+  uint32_t m; uint32_t* sw = split_word (p, n, m);
+  atomicAnd (sw, ~m);                                                // children.clear ()
+  int cs = children_slot (p, n, false);
+  if (cs >= 0) for (int c = 0; c < 8; ++c) reset_node (p, make_child (p, n, c, cs));
+  if (e.kind == KIND_NEW)
+  {
+    Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);                // same observation as in the down sweep
+    bool updated;
+    int rc = leaf_update (p, f, n, o, updated);                      // hpp:189-214 (falls through after :181)
+    upd += updated;
+    return rc;
+  }
+  if (defer_slow) return RC_DEFERRED;
+  return upper_fold_slow (p, f, n, upd, vis);                        // pre-existing children pruned: leaf visit, may re-split
+}
+
+template <int NL>   // NL = number of levels below the coarse cell down to the block roots (1..3)
+__global__ void __launch_bounds__ (CELL_THREADS) k_cell_down (Params p, Frame f, const QNode* __restrict__ cells, const int* __restrict__ ncells,
+                                                             QNode* __restrict__ gq, CellRecord* __restrict__ recs, int cell_cap,
+                                                             int* __restrict__ blist, int* __restrict__ bcount, unsigned long long* __restrict__ stats)
+{
+  constexpr int CAP1 = 8, CAP2 = NL >= 2 ? 64 : 1, CAP3 = NL >= 3 ? 512 : 1;
+  constexpr int STRIDE = 1 + 8 + (NL >= 2 ? 64 : 0) + (NL >= 3 ? 512 : 0);
+  __shared__ QNode q0, q1[CAP1], q2[CAP2], q3[CAP3];
+  __shared__ int cnt[4];
+  unsigned long long upd = 0, vis = 0;
+  const int tid = threadIdx.x;
+  int count = *ncells;
+  if (count > cell_cap) { if (tid == 0 && blockIdx.x == 0) raise_err (p, ERR_QUEUE_FULL); count = cell_cap; }
+  for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
+  {
+    __syncthreads ();
+    if (tid < 4) cnt[tid] = 0;
+    __syncthreads ();
+    QNode* lvq[4] = { &q0, q1, q2, q3 };
+    if (tid == 0) { q0 = cells[ci]; cnt[0] = 1; }
+    __syncthreads ();
+#pragma unroll
+    for (int rl = 0; rl <= NL; ++rl)
+    {
+      const int level = p.C + rl;
+      const int n_here = cnt[rl];
+      const bool block_level = (rl == NL);
+      for (int base = 0; base < n_here; base += CELL_THREADS)          // warp-uniform trip count
+      {
+        const int i = base + tid;
+        const bool active = i < n_here;
+        QNode e; NodePos n; int cs = -1; int interior = 0;
+        if (active) { e = lvq[rl][i]; vis++; interior = upper_visit (p, f, level, e, n, cs, upd); }
+        if (!block_level)
+        {
+          if (active && interior)
+          {
+            int b = atomicAdd (&cnt[rl + 1], 8);
+            e.child_base = b;
+            for (int c = 0; c < 8; ++c)
+            {
+              NodePos ch = make_child (p, n, c, cs);
+              QNode q; q.x = ch.x; q.y = ch.y; q.z = ch.z; q.slot = ch.slot; q.idx = ch.idx; q.kind = KIND_DONE; q.child_base = -1; q.rc = 0;
+              lvq[rl + 1][b + c] = q;
+            }
+          }
+        }
+        else
+        {
+          // interior block roots -> global block list; the entry index is the node's slot in this cell's record
+          const unsigned lane = tid & 31;
+          const unsigned mask = __ballot_sync (0xffffffffu, active && interior);
+          if (mask)
+          {
+            int b = 0;
+            const int leader = __ffs (mask) - 1;
+            if ((int) lane == leader) b = atomicAdd (bcount, __popc (mask));
+            b = __shfl_sync (0xffffffffu, b, leader);
+            if (active && interior)
+            {
+              e.child_base = cs;
+              blist[b + __popc (mask & ((1u << lane) - 1))] = ci * STRIDE + (NL == 1 ? 1 : (NL == 2 ? 9 : 73)) + i;
+            }
+          }
+        }
+        if (active) lvq[rl][i] = e;
+      }
+      __syncthreads ();
+    }
+    // spill this cell's queues for the block kernel and the bottom-up sweep
+    QNode* g = gq + (size_t) ci * STRIDE;
+    if (tid == 0) { g[0] = q0; recs[ci].n[0] = 1; recs[ci].n[1] = cnt[1]; recs[ci].n[2] = NL >= 2 ? cnt[2] : 0; recs[ci].n[3] = NL >= 3 ? cnt[3] : 0; }
+    for (int i = tid; i < cnt[1]; i += CELL_THREADS) g[1 + i] = q1[i];
+    if (NL >= 2) for (int i = tid; i < cnt[2]; i += CELL_THREADS) g[9 + i] = q2[i];
+    if (NL >= 3) for (int i = tid; i < cnt[3]; i += CELL_THREADS) g[73 + i] = q3[i];
+  }
+  __syncwarp ();
+  warp_add_stats (stats, upd, vis);
+}
+
+template <int NL>
+__global__ void __launch_bounds__ (CELL_THREADS) k_cell_up (Params p, Frame f, const int* __restrict__ ncells, QNode* __restrict__ gq,
+                                                           const CellRecord* __restrict__ recs, int cell_cap, unsigned long long* __restrict__ stats)
+{
+  constexpr int STRIDE = 1 + 8 + (NL >= 2 ? 64 : 0) + (NL >= 3 ? 512 : 0);
+  const int off[4] = { 0, 1, 9, 73 };
+  __shared__ int slow[64];
+  __shared__ int nslow;
+  unsigned long long upd = 0, vis = 0;
+  const int tid = threadIdx.x;
+  int count = *ncells;
+  if (count > cell_cap) count = cell_cap;
+  for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
+  {
+    QNode* g = gq + (size_t) ci * STRIDE;
+    const CellRecord r = recs[ci];
+    for (int rl = NL - 1; rl >= 0; --rl)
+    {
+      if (tid == 0) nslow = 0;
+      __syncthreads ();                                                // child return codes of level rl+1 are final
+      const int level = p.C + rl;
+      for (int i = tid; i < r.n[rl]; i += CELL_THREADS)
+      {
+        QNode e = g[off[rl] + i];
+        if (e.kind == KIND_DONE) continue;
+        const QNode* ch = g + off[rl + 1] + e.child_base;
+        bool all_empty = true;
+        for (int c = 0; c < 8; ++c) all_empty &= (ch[c].rc < 0);
+        int rc = upper_fold (p, f, level, e, all_empty, upd, vis, true);
+        if (rc == RC_DEFERRED) slow[atomicAdd (&nslow, 1)] = i;         // at most 64 interior nodes per level per cell
+        else g[off[rl] + i].rc = rc;
+      }
+      __syncthreads ();
+      // the rare leaf-visit-after-prune cases: one warp, eight children in parallel
+      if (tid < 32)
+        for (int k = 0; k < nslow; ++k)
+        {
+          const int i = slow[k];
+          const QNode e = g[off[rl] + i];
+          NodePos n = qnode_pos (p, level, e);
+          int rc = leaf_visit_warp8 (p, f, n, upd, vis);
+          if (tid == 0) g[off[rl] + i].rc = rc;
+        }
+      __threadfence_block ();
+      __syncthreads ();
+    }
+  }
+  __syncwarp ();
+  warp_add_stats (stats, upd, vis);
+}
+
 // ---- 2. one warp per interior block root ------------------------------------------------------------------
 // Block roots (level B = L-3) are evaluated by k_upper_down like every other upper node; only the
 // ones that have (or get) children are appended to the block list, with the brick slot cached in

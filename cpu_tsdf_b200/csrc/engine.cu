@@ -285,6 +285,8 @@ struct b200tsdf
   // fast-path work queues (levels C .. L-3)
   Queues Q{}; int q_levels = 0; QNode* q_mem = nullptr; size_t q_mem_cap = 0;
   int* d_blist = nullptr; int* d_bail = nullptr; size_t blist_cap = 0;
+  // fused per-cell upper sweeps (coarse cells are the top-tier roots and the block roots are <= 3 levels below)
+  bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0;
   bool fast_path = false; int force_general = 0;
   // measurement
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
@@ -371,6 +373,7 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   for (int i = 0; ok && i < KRING; ++i)
     ok = cudaEventCreate (&h->kring[i][0]) == cudaSuccess && cudaEventCreate (&h->kring[i][1]) == cudaSuccess;
   if (ok) { cudaMemset (h->d_err, 0, sizeof (int)); cudaMemset (h->d_stats, 0, ST_TOTAL * sizeof (unsigned long long)); }
+  if (ok) { unsigned long long* dp = h->d_stats + 3; ok = cudaMemcpyToSymbol (g_diag, &dp, sizeof (dp)) == cudaSuccess; }
   // the depth-first general path recurses up to (L - C + 1) levels
   if (ok) cudaDeviceSetLimit (cudaLimitStackSize, 16384);
   if (!ok) { b200tsdf_destroy (h); return B200TSDF_ECUDA; }
@@ -386,7 +389,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
   free_volume (h);
   cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled);
-  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail);
+  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
   if (h->ev_k0) cudaEventDestroy (h->ev_k0); if (h->ev_k1) cudaEventDestroy (h->ev_k1);
@@ -475,7 +478,25 @@ int b200tsdf_reset (b200tsdf_t* h)
     for (int i = 0; i < MAX_QLEVELS; ++i) { h->Q.q[i] = nullptr; h->Q.cap[i] = 0; }
     for (int i = 0; i < h->q_levels; ++i) { h->Q.q[i] = h->q_mem + off; h->Q.cap[i] = (int) caps[i]; off += caps[i]; }
     h->Q.n = h->d_count;
+    // per-cell path
+    h->cell_nl = Bl - np.C;
+    h->cell_path = h->fast_path && np.Rtop == np.C && h->cell_nl >= 1 && h->cell_nl <= 3 && !(c.reserved[0] & 2);
+    if (h->cell_path)
+    {
+      size_t ncell = (size_t) 1 << (3 * np.C);
+      h->cell_cap = (int) std::min (ncell, (size_t) 16384);
+      size_t stride = h->cell_nl == 1 ? 9 : (h->cell_nl == 2 ? 73 : 585);
+      size_t need = (size_t) h->cell_cap * stride;
+      if (need > h->cellq_cap)
+      {
+        cudaFree (h->d_cellq); cudaFree (h->d_cellrec); h->d_cellq = nullptr; h->d_cellrec = nullptr; h->cellq_cap = 0;
+        CK (cudaMalloc (&h->d_cellq, need * sizeof (QNode)));
+        CK (cudaMalloc (&h->d_cellrec, (size_t) h->cell_cap * sizeof (CellRecord)));
+        h->cellq_cap = need;
+      }
+    }
     size_t bl = h->q_levels ? caps[h->q_levels - 1] : 0;
+    if (h->cell_path) bl = std::max (bl, (size_t) h->cell_cap * 512);
     if (bl > h->blist_cap)
     {
       cudaFree (h->d_blist); cudaFree (h->d_bail); h->d_blist = h->d_bail = nullptr; h->blist_cap = 0;
@@ -540,14 +561,36 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   {
     const int nl = h->q_levels;
     int* d_bcount = h->d_count + 9; int* d_bailcount = h->d_count + 10;
-    for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
+    Queues Qb = h->Q;
+    int bli = nl - 1;
+    if (h->cell_path)
+    {
+      const int NL = h->cell_nl;
+      Qb.q[NL] = h->d_cellq; Qb.cap[NL] = (int) std::min (h->cellq_cap, (size_t) 0x7fffffff);
+      bli = NL;
+      if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      else k_cell_down<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      h->launches++;
+    }
+    else
+      for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
     CK (cudaEventRecord (h->kring[kr][0], s));
-    if (p.color) k_blocks<true><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
-    else k_blocks<false><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, h->Q, nl - 1, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
+    if (p.color) k_blocks<true><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
+    else k_blocks<false><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
     CK (cudaEventRecord (h->kring[kr][1], s));
-    k_bail<<<8, 64, 0, s>>> (p, f, h->Q, nl - 1, h->d_bail, d_bailcount, h->d_stats);
+    k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats);
     h->launches += 2;
-    for (int li = nl - 2; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
+    if (h->cell_path)
+    {
+      const int NL = h->cell_nl;
+      if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      else k_cell_up<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      h->launches++;
+    }
+    else
+      for (int li = nl - 2; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
   }
   else
   {
@@ -637,6 +680,8 @@ int b200tsdf_get_stats (b200tsdf_t* h, b200tsdf_stats* s)
   s->n_updates = (int64_t) (st[ST_UPDATES] - st[ST_N + ST_UPDATES]);
   s->n_node_visits = (int64_t) (st[ST_VISITS] - st[ST_N + ST_VISITS]);
   s->n_block_visits = (int64_t) (st[ST_BLOCKS] - st[ST_N + ST_BLOCKS]);
+  s->reserved = (int32_t) (st[3] - st[ST_N + 3]);          // diagnostics: slow folds in the last frame
+  s->n_bail = cnt[10]; s->n_slow_visits = (int64_t) (st[4] - st[ST_N + 4]);
   s->n_culled_cells = cnt[0];
   s->pool_capacity = (int64_t) h->pool;
   s->coarse_level = h->p.C; s->finest_level = h->p.L; s->tiers = h->p.T;

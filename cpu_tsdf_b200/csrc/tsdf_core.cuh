@@ -138,6 +138,7 @@ struct Params
   int color, track_var;
   // sharding: this device owns coarse cells with cell_hash % shard_count == shard_rank
   int shard_rank, shard_count;
+  int debug;                  // experiment switches (B200TSDF_DEBUG); 0 in normal operation
   // storage
   uint64_t* keys;             // [pool]
   uint32_t pool_mask;
@@ -537,6 +538,60 @@ struct Counters { long long n_updates, n_visits; };
 // This is the general path: it handles every case including prune-then-resplit.
 // The brick-parallel kernels in engine.cu are the fast path for the common cases and fall back
 // to this routine per subtree.
+//
+// split_and_expand is hpp:161-188 for a leaf that splits now: its eight children are FRESH by the
+// storage invariant, so their state is known without loading it, and their observations do not
+// depend on each other — all eight depth lookups are issued before any child is processed, which
+// keeps the (latency-bound) general path short.
+B2_HDN inline bool split_and_expand (const Params& p, const Frame& f, const NodePos& n, uint32_t* sw, uint32_t smask, Counters& cnt);
+
+B2_HDN inline int visit_fresh_leaf (const Params& p, const Frame& f, const NodePos& n, const Obs& o, Counters& cnt)
+{
+  cnt.n_visits++;
+  if (!o.valid) return 0;
+  if (o.near_ && n.size > p.finest_size)
+  {
+    uint32_t smask = 0; uint32_t* sw = split_word (p, n, smask);
+    if (split_and_expand (p, f, n, sw, smask, cnt)) return 1;
+  }
+  // leaf update of a node known to be in the constructor state (octree.h:71-74)
+  float2 dw = make_float2 (-1.f, 0.f); uchar4 c = make_uchar4 (0, 0, 0, 0); float M = 0.f; int ns = 0;
+  bool updated;
+  int rc = leaf_update_values (p, f, o, dw, c, M, ns, updated);
+  if (updated)
+  {
+    cnt.n_updates++;
+    *node_dw (p, n) = dw;
+    if (p.color) { if (n.slot < 0) p.root_rgb[n.idx] = c; else p.rgb[(size_t) n.slot * BRICK_NODES + n.idx] = c; }
+    if (p.track_var)
+    {
+      if (n.slot < 0) { p.root_M[n.idx] = M; p.root_ns[n.idx] = ns; }
+      else { p.M[(size_t) n.slot * BRICK_NODES + n.idx] = M; p.ns[(size_t) n.slot * BRICK_NODES + n.idx] = ns; }
+    }
+  }
+  return rc;
+}
+
+// returns true if the node stays split (some child is non-empty), false if the children were pruned again
+B2_HDN inline bool split_and_expand (const Params& p, const Frame& f, const NodePos& n, uint32_t* sw, uint32_t smask, Counters& cnt)
+{
+  int cs = children_slot (p, n, true);
+  if (cs < 0) return false;
+  atomic_or32 (sw, smask);                                       // split (): children are fresh by invariant
+  NodePos ch[8]; Obs oc[8];
+  for (int c = 0; c < 8; ++c)
+  {
+    ch[c] = make_child (p, n, c, cs);
+    oc[c] = observe (p, f, ch[c].cx, ch[c].cy, ch[c].cz, ch[c].size);
+  }
+  bool all_empty = true;
+  for (int c = 0; c < 8; ++c) all_empty &= (visit_fresh_leaf (p, f, ch[c], oc[c], cnt) < 0);
+  if (!all_empty) return true;
+  atomic_and32 (sw, ~smask);                                     // children.clear ()
+  for (int c = 0; c < 8; ++c) reset_node (p, ch[c]);
+  return false;
+}
+
 B2_HDN inline int update_voxel_dfs (const Params& p, const Frame& f, const NodePos& n, Counters& cnt)
 {
   cnt.n_visits++;
@@ -556,17 +611,7 @@ B2_HDN inline int update_voxel_dfs (const Params& p, const Frame& f, const NodeP
   Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
   if (!o.valid) return 0;
   if (o.near_ && n.size > p.finest_size)                         // hpp:161-188
-  {
-    int cs = children_slot (p, n, true);
-    if (cs < 0) return 0;
-    atomic_or32 (sw, smask);                                     // split (): children are fresh by invariant
-    bool all_empty = true;
-    for (int c = 0; c < 8; ++c)
-      all_empty &= (update_voxel_dfs (p, f, make_child (p, n, c, cs), cnt) < 0);
-    if (!all_empty) return 1;
-    atomic_and32 (sw, ~smask);
-    for (int c = 0; c < 8; ++c) reset_node (p, make_child (p, n, c, cs));
-  }
+    if (split_and_expand (p, f, n, sw, smask, cnt)) return 1;
   bool updated;
   int rc = leaf_update (p, f, n, o, updated);
   if (updated) cnt.n_updates++;

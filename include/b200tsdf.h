@@ -50,7 +50,7 @@ typedef struct b200tsdf_config
   int32_t device;                           /* CUDA device ordinal                                */
   int32_t pool_log2;                        /* brick pool capacity = 2^pool_log2 (0 = default 20) */
   int32_t shard_rank, shard_count;          /* this handle owns coarse cells with hash(cell) % shard_count == shard_rank */
-  int32_t reserved[4];                      /* [0] bit0: debug — use only the general depth-first update kernel */
+  int32_t reserved[4];                      /* [0] debug — bit0: general depth-first update kernel only; bit1: per-level upper sweeps instead of the fused per-cell ones */
   double  global_transform[16];             /* setGlobalTransform tsdf_volume_octree.h:119; row-major 4x4 */
 } b200tsdf_config;
 
@@ -124,9 +124,11 @@ typedef struct b200tsdf_stats
   int64_t n_bricks;         /* allocated bricks */
   int64_t n_block_visits;   /* finest-tier bricks processed in the last frame */
   int64_t pool_capacity;
-  int32_t coarse_level, finest_level, tiers, reserved;
+  int32_t coarse_level, finest_level, tiers, reserved;   /* reserved: upper-level slow folds in the last frame */
   double  ms_last_integrate;   /* device time of the last integrate (CUDA events on the handle's stream) */
   double  ms_last_kernel;      /* device time of the dominant (brick update) kernel in the last integrate */
+  int64_t n_bail;              /* block roots handed to the general path in the last frame (prune-then-resplit) */
+  int64_t n_slow_visits;       /* node visits made by the general path inside the upper sweeps in the last frame */
 } b200tsdf_stats;
 int  b200tsdf_get_stats (b200tsdf_t* h, b200tsdf_stats* s);
 
