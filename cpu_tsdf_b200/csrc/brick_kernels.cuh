@@ -516,10 +516,13 @@ __device__ __forceinline__ bool fallthrough_node (const Params& p, const Frame& 
 }
 
 template <bool COLOR>
-__global__ void __launch_bounds__ (BLK_WARPS * 32, 4) k_blocks (Params p, Frame f, Queues Q, int li,
+#ifndef B2_BLK_MINB
+#define B2_BLK_MINB 6
+#endif
+__global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params p, Frame f, Queues Q, int li,
                                                                 const int* __restrict__ blist, const int* __restrict__ bcount,
                                                                 int* __restrict__ bail, int* __restrict__ bail_count,
-                                                                unsigned long long* __restrict__ stats)
+                                                                int* __restrict__ next_work, unsigned long long* __restrict__ stats)
 {
   __shared__ __align__ (16) WarpSmem smem[BLK_WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -532,8 +535,14 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32, 4) k_blocks (Params p, Frame 
   const float off1 = sizeB * 0.25f;
   const double thr1 = near_threshold (sizeB * 0.5f), thr2 = near_threshold (sizeB * 0.25f);
 
-  for (int wi = blockIdx.x * BLK_WARPS + wib; wi < count; wi += nwarps)
+  // persistent grid (one resident wave); warps pull bricks from a shared counter so the tail stays short
+  (void) nwarps;
+  for (;;)
   {
+    int wi = 0;
+    if (lane == 0) wi = atomicAdd (next_work, 1);
+    wi = __shfl_sync (0xffffffffu, wi, 0);
+    if (wi >= count) break;
     const int qi = blist[wi];
     const QNode e = Q.q[li][qi];
     nblk += (lane == 0);

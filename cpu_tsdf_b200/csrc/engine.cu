@@ -267,7 +267,7 @@ struct b200tsdf
   b200tsdf_config cfg_pending{}, cfg{};
   bool has_volume = false;
   Params p{};
-  int device = 0;
+  int device = 0, sm_count = 148;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   size_t pool = 0;
   bool alloc_color = false, alloc_var = false;
@@ -359,6 +359,7 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   h->device = h->cfg_pending.device;
   if (h->device < 0 || h->device >= ndev) { delete h; return B200TSDF_EINVAL; }
   bool ok = cudaSetDevice (h->device) == cudaSuccess
+         && cudaDeviceGetAttribute (&h->sm_count, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess
          && cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking) == cudaSuccess
          && cudaStreamCreateWithFlags (&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess
          && cudaMalloc (&h->d_err, sizeof (int)) == cudaSuccess
@@ -576,8 +577,8 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
     else
       for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
     CK (cudaEventRecord (h->kring[kr][0], s));
-    if (p.color) k_blocks<true><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
-    else k_blocks<false><<<148 * 8, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_stats);
+    if (p.color) k_blocks<true><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_count + 11, h->d_stats);
+    else k_blocks<false><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_count + 11, h->d_stats);
     CK (cudaEventRecord (h->kring[kr][1], s));
     k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats);
     h->launches += 2;

@@ -474,21 +474,21 @@ B2_HD Obs observe (const Params& p, const Frame& f, float cx, float cy, float cz
 // truncation + addObservation + return code (hpp:189-214, octree.cpp:152-163, :328-337) on VALUES:
 // dw / c / M / ns are the node's state (in registers, shared memory or wherever the caller staged
 // it).  Returns 1 / 0 / -1 like updateVoxel; `updated` says whether the state changed.
-B2_HD int leaf_update_values (const Params& p, const Frame& f, const Obs& o, float2& dw, uchar4& c, float& M, int& ns, bool& updated)
+// (bgra = the PCL colour word of the observed pixel, bytes b,g,r,a; used when have_bgra)
+B2_HD int leaf_update_core (const Params& p, float d_new, bool have_bgra, uint32_t bgra, float2& dw, uchar4& c, float& M, int& ns, bool& updated)
 {
   updated = false;
-  float d_new = o.d_new;
   if (d_new > p.max_dist_pos) d_new = p.max_dist_pos;
   else if (d_new < -p.max_dist_neg) return 0;
   d_new = fdiv (d_new, p.max_dist_neg);
   const float w_new = 1.f;
-  if (p.color && f.rgba_off >= 0)
+  if (p.color && have_bgra)
   {
-    const unsigned char* bgr = frame_bgr (f, o.u, o.v);
+    const float cb = (float) (bgra & 0xFFu), cg = (float) ((bgra >> 8) & 0xFFu), cr = (float) ((bgra >> 16) & 0xFFu);
     float wsum = fadd (dw.y, w_new);
-    c.x = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.x), fmul (w_new, (float) bgr[2])), wsum);   // r
-    c.y = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.y), fmul (w_new, (float) bgr[1])), wsum);   // g
-    c.z = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.z), fmul (w_new, (float) bgr[0])), wsum);   // b
+    c.x = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.x), fmul (w_new, cr)), wsum);   // r
+    c.y = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.y), fmul (w_new, cg)), wsum);   // g
+    c.z = (unsigned char) fdiv (fadd (fmul (dw.y, (float) c.z), fmul (w_new, cb)), wsum);   // b
   }
   float d_old = dw.x;
   float d = fdiv (fadd (fmul (dw.x, dw.y), fmul (d_new, w_new)), fadd (dw.y, w_new));
@@ -504,6 +504,14 @@ B2_HD int leaf_update_values (const Params& p, const Frame& f, const Obs& o, flo
   if ((double) d < -0.99) return 0;
   else if ((double) d < p.rc_thresh) return 1;
   else return -1;
+}
+
+B2_HD int leaf_update_values (const Params& p, const Frame& f, const Obs& o, float2& dw, uchar4& c, float& M, int& ns, bool& updated)
+{
+  bool have = p.color && f.rgba_off >= 0;
+  uint32_t bgra = 0;
+  if (have) { const unsigned char* b = frame_bgr (f, o.u, o.v); bgra = (uint32_t) b[0] | ((uint32_t) b[1] << 8) | ((uint32_t) b[2] << 16) | ((uint32_t) b[3] << 24); }
+  return leaf_update_core (p, o.d_new, have, bgra, dw, c, M, ns, updated);
 }
 
 // the same on a node in global storage
