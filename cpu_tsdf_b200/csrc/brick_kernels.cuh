@@ -211,7 +211,7 @@ __global__ void k_upper_up (Params p, Frame f, Queues Q, int li, unsigned long l
 // the whole upper pyramid of one coarse cell (1 + 8 + 64 nodes + up to 512 block roots) fits in shared memory.
 // k_cell_down walks it level by level inside one CTA (a __syncthreads between levels instead of a kernel
 // launch) and k_cell_up folds it back.  Same per-node rules as k_upper_down / k_upper_up.
-constexpr int CELL_THREADS = 128;
+constexpr int CELL_THREADS = 256;
 struct CellRecord { int n[4]; };                 // entries per relative level 0..3 for this cell
 
 __device__ __forceinline__ int upper_visit (const Params& p, const Frame& f, int level, QNode& e, NodePos& n, int& cs,
@@ -413,6 +413,16 @@ __global__ void __launch_bounds__ (CELL_THREADS) k_cell_up (Params p, Frame f, c
   {
     QNode* g = gq + (size_t) ci * STRIDE;
     const CellRecord r = recs[ci];
+    // block roots that k_blocks handed back (prune-then-resplit inside the block, nothing committed):
+    // redo them with the general depth-first routine before their parents are folded
+    for (int i = tid; i < r.n[NL]; i += CELL_THREADS)
+    {
+      const QNode e = g[off[NL] + i];
+      if (e.rc != RC_DEFERRED) continue;
+      NodePos n = qnode_pos (p, p.C + NL, e);
+      if (e.kind == KIND_NEW) { uint32_t m; uint32_t* sw = split_word (p, n, m); atomicAnd (sw, ~m); }   // undo the speculative split
+      g[off[NL] + i].rc = upper_fold_slow (p, f, n, upd, vis);
+    }
     for (int rl = NL - 1; rl >= 0; --rl)
     {
       if (tid == 0) nslow = 0;
@@ -704,7 +714,7 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params
     if (__any_sync (0xffffffffu, bail_f))
     {
       // nothing has been committed: hand this block root to the general depth-first routine (k_bail)
-      if (lane == 0) bail[atomicAdd (bail_count, 1)] = qi;
+      if (lane == 0) { if (bail) bail[atomicAdd (bail_count, 1)] = qi; else { Q.q[li][qi].rc = RC_DEFERRED; atomicAdd (bail_count, 1); } }
       __syncwarp ();
       continue;
     }

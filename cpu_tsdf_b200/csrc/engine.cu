@@ -107,6 +107,48 @@ __global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restr
   }
 }
 
+// frame front end in ONE launch: blocks [0, cull_blocks) run the frustum cull of the coarse cells, the
+// rest the per-pixel pre-split.  The two are independent (the cull reads only geometry).  The work-list
+// counters and the statistics snapshot are reset by k_frame_begin on the previous launch boundary.
+__global__ void k_front (Params p, Frame f, Planes P, int cull_blocks, int* __restrict__ list, int* __restrict__ count, QNode* __restrict__ q0)
+{
+  if ((int) blockIdx.x < cull_blocks)
+  {
+    int n = 1 << p.C;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n * n) return;
+    int z = i % n, y = (i / n) % n, x = i / (n * n);
+    float cx = center1d (p, p.C, x), cy = center1d (p, p.C, y), cz = center1d (p, p.C, z);
+    if (!frustum_contains (P.pl, cx, cy, cz) || !owns_cell (p, x, y, z)) return;
+    int k = atomicAdd (count, 1);
+    list[k] = i;
+    if (q0)
+    {
+      NodePos nd;
+      if (!locate_node (p, p.C, x, y, z, nd)) { raise_err (p, ERR_MISSING_BRICK); nd.slot = -1; nd.idx = 0; }
+      QNode e; e.x = x; e.y = y; e.z = z; e.slot = nd.slot; e.idx = nd.idx; e.kind = KIND_DONE; e.child_base = -1; e.rc = 0;
+      q0[k] = e;
+    }
+    return;
+  }
+  int i = (blockIdx.x - cull_blocks) * blockDim.x + threadIdx.x;
+  if (i >= f.width * f.height) return;
+  int u = i % f.width, v = i / f.width;
+  const float* pt = frame_xyz (f, u, v);
+  float z = pt[2];
+  if (is_nan (z)) return;                                        // hpp:64
+  float pw[3];
+  affine_mul_f (f.tfwd, pt[0], pt[1], z, pw);                    // hpp:76
+  int fx_, fy_, fz_;
+  if (!world_to_finest (p, pw[0], pw[1], pw[2], fx_, fy_, fz_)) return;
+  if (p.shard_count > 1)
+  {
+    int sh = p.L - p.C;
+    if (!owns_cell (p, fx_ >> sh, fy_ >> sh, fz_ >> sh)) return;
+  }
+  presplit_point (p, fx_, fy_, fz_);
+}
+
 // general path: one thread per culled coarse cell runs updateVoxel depth-first
 __global__ void k_update_dfs (Params p, Frame f, const int* __restrict__ list, const int* __restrict__ count, unsigned long long* __restrict__ stats)
 {
@@ -551,10 +593,12 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   CK (cudaEventRecord (h->ev_t0, s));
   k_frame_begin<<<1, 32, 0, s>>> (h->d_stats, h->d_count);
   int npix = W * H;
-  k_presplit<<<(npix + 255) / 256, 256, 0, s>>> (p, f);
   int ncells = 1 << (3 * p.C);
-  k_cull<<<(ncells + 127) / 128, 128, 0, s>>> (p, P, h->d_culled, h->d_count, nullptr, h->fast_path ? h->Q.q[0] : nullptr);
-  h->launches += 3;
+  {
+    const int cull_blocks = (ncells + 255) / 256;
+    k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, f, P, cull_blocks, h->d_culled, h->d_count, h->fast_path ? h->Q.q[0] : nullptr);
+  }
+  h->launches += 2;
   // dominant kernel, bracketed by a ring of event pairs so bench.py can average its launch duration
   if (h->kring_pending >= KRING) h->drain_kring (KRING / 2);
   int kr = h->kring_head;
@@ -577,11 +621,12 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
     else
       for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
     CK (cudaEventRecord (h->kring[kr][0], s));
-    if (p.color) k_blocks<true><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_count + 11, h->d_stats);
-    else k_blocks<false><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, h->d_bail, d_bailcount, h->d_count + 11, h->d_stats);
+    int* bail_list = h->cell_path ? nullptr : h->d_bail;       // the per-cell bottom-up sweep redoes deferred block roots itself
+    if (p.color) k_blocks<true><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, h->d_count + 11, h->d_stats);
+    else k_blocks<false><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, h->d_count + 11, h->d_stats);
     CK (cudaEventRecord (h->kring[kr][1], s));
-    k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats);
-    h->launches += 2;
+    h->launches++;
+    if (!h->cell_path) { k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats); h->launches++; }
     if (h->cell_path)
     {
       const int NL = h->cell_nl;
