@@ -165,9 +165,21 @@ __global__ void k_update_dfs (Params p, Frame f, const int* __restrict__ list, c
   atomicAdd (&stats[ST_VISITS], (unsigned long long) cnt.n_visits);
 }
 
-__global__ void k_query (Params p, const float* __restrict__ xyz, int n, int what, int mode,
+// read-side kernels keep Params in shared memory (see find_leaf in tsdf_core.cuh)
+#define B2_STAGE_PARAMS(gp)                                                     \
+  __shared__ Params sp_;                                                        \
+  {                                                                             \
+    const int* src_ = reinterpret_cast<const int*> (&gp);                       \
+    int* dst_ = reinterpret_cast<int*> (&sp_);                                  \
+    for (int w_ = threadIdx.x; w_ < (int) (sizeof (Params) / sizeof (int)); w_ += blockDim.x) dst_[w_] = src_[w_]; \
+  }                                                                             \
+  __syncthreads ();                                                             \
+  const Params& p = sp_;
+
+__global__ void k_query (Params gp, const float* __restrict__ xyz, int n, int what, int mode,
                          float* val, float* grad, float* hess, unsigned char* ok)
 {
+  B2_STAGE_PARAMS (gp)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v, g[3], hs[9];
@@ -179,8 +191,9 @@ __global__ void k_query (Params p, const float* __restrict__ xyz, int n, int wha
   if (what & 4) for (int k = 0; k < 9; ++k) hess[9 * i + k] = hs[k];
 }
 
-__global__ void k_render (Params p, RenderParams r, float* __restrict__ out /* 6 floats per pixel */, unsigned char* __restrict__ rgb)
+__global__ void k_render (Params gp, RenderParams r, float* __restrict__ out /* 6 floats per pixel */, unsigned char* __restrict__ rgb)
 {
+  B2_STAGE_PARAMS (gp)
   // 8x8 pixel tiles keep neighbouring rays in one warp-pair
   int tx = threadIdx.x % 8, ty = threadIdx.x / 8;
   int x = blockIdx.x * 8 + tx, y = blockIdx.y * 8 + ty;
@@ -226,9 +239,10 @@ __device__ __forceinline__ bool brick_root_is_split (const Params& p, int t, int
 }
 
 template <bool EMIT>
-__global__ void k_mesh_bricks (Params p, McParams mc, const int* __restrict__ list, int nbricks,
+__global__ void k_mesh_bricks (Params gp, McParams mc, const int* __restrict__ list, int nbricks,
                                unsigned long long* __restrict__ total, float* __restrict__ verts, unsigned char* __restrict__ cols)
 {
+  B2_STAGE_PARAMS (gp)
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= nbricks) return;
@@ -284,8 +298,9 @@ __global__ void k_mesh_bricks (Params p, McParams mc, const int* __restrict__ li
 
 // leaves held in the root arrays (unsplit coarse cells when Rtop == C)
 template <bool EMIT>
-__global__ void k_mesh_roots (Params p, McParams mc, unsigned long long* __restrict__ total, float* __restrict__ verts, unsigned char* __restrict__ cols)
+__global__ void k_mesh_roots (Params gp, McParams mc, unsigned long long* __restrict__ total, float* __restrict__ verts, unsigned char* __restrict__ cols)
 {
+  B2_STAGE_PARAMS (gp)
   int n = 1 << p.Rtop;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * n * n || p.Rtop < p.C) return;

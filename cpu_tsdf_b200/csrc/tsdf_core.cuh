@@ -688,7 +688,7 @@ B2_HD void presplit_point (const Params& p, int fx_, int fy_, int fz_)
 // ---- getContainingVoxel over the flat layout (octree.cpp:112-121, :628-634) --------------------
 struct Leaf { bool found; NodePos n; float d, w; };
 
-B2_HD Leaf find_leaf (const Params& p, float x, float y, float z)
+B2_HD Leaf find_leaf_impl (const Params& p, float x, float y, float z)
 {
   Leaf lf; lf.found = false;
   if (is_nan (z) || fabsf (x) > p.half || fabsf (y) > p.half || fabsf (z) > p.half) return lf;
@@ -718,6 +718,16 @@ B2_HD Leaf find_leaf (const Params& p, float x, float y, float z)
   lf.found = true; lf.n = n; lf.d = dw.x; lf.w = dw.y;
   return lf;
 }
+
+// On the device the descent is ONE out-of-line routine: renderView / queries / marching cubes call it ~70
+// times per item, and inlining every call made those kernels ~40k instructions (instruction-cache bound).
+// Callers stage Params in shared memory so the reference they pass does not force a local copy.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ void find_leaf_out (const Params& p, float x, float y, float z, Leaf* out) { *out = find_leaf_impl (p, x, y, z); }
+B2_HD Leaf find_leaf (const Params& p, float x, float y, float z) { Leaf l; find_leaf_out (p, x, y, z, &l); return l; }
+#else
+B2_HD Leaf find_leaf (const Params& p, float x, float y, float z) { return find_leaf_impl (p, x, y, z); }
+#endif
 
 // ---- getVoxelCenter / getVoxelIndex (tsdf_volume_octree.cpp:553-574) ----------------------------
 B2_HD float voxel_center1 (const Params& p, long long i)
