@@ -466,12 +466,39 @@ __global__ void __launch_bounds__ (CELL_THREADS) k_cell_up (Params p, Frame f, c
 // back only what changed.
 constexpr int BLK_WARPS = 4;
 
+// ---- TMA (bulk async copy) staging of a brick: cp.async.bulk global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t) __cvta_generic_to_shared (p); }
+__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
+{ asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
+{ asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s (void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                :: "r"(smem_u32 (dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
+}
+// bounded wait: a protocol mistake must not be able to hang the device
+__device__ __forceinline__ bool mbar_wait (uint64_t* bar, uint32_t parity)
+{
+  for (int it = 0; it < (1 << 22); ++it)
+  {
+    uint32_t done;
+    asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                  : "=r"(done) : "r"(smem_u32 (bar)), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void fence_proxy_async_smem () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct WarpSmem
 {
   float2 dw[BRICK_NODES];       // 4672 B
   uchar4 rgb[BRICK_NODES];      // 2336 B (colour volumes only)
   float dnew[72];               // saved observation of level-1/2 nodes split this frame (fall-through update)
   int uv[72];
+  uint64_t bar;                 // mbarrier of this warp's TMA staging
+  uint64_t pad_;
 };
 
 __device__ __forceinline__ void path_center (const float* c0, float off, int k, int j, float* c)
@@ -537,6 +564,9 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params
   __shared__ __align__ (16) WarpSmem smem[BLK_WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpSmem& S = smem[wib];
+  if (lane == 0) { mbar_init (&S.bar, 1); asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncwarp ();
+  uint32_t tma_phase = 0;
   const int B = p.C + li;
   const int count = *bcount;
   const int nwarps = gridDim.x * BLK_WARPS;
@@ -561,23 +591,20 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params
     float2* gdw = p.nodes + (size_t) bslot * BRICK_NODES;
     uchar4* grgb = COLOR ? p.rgb + (size_t) bslot * BRICK_NODES : nullptr;
     uint32_t* gsw = p.split + (size_t) bslot * BRICK_SPLIT_WORDS;
-    // ---- stage the brick with 16-byte loads ----
+    // ---- stage the brick with the TMA: one bulk copy per array, completion on the warp's mbarrier ----
     __syncwarp ();
+    if (lane == 0)
     {
-      const float4* g4 = reinterpret_cast<const float4*> (gdw);
-      float4* s4 = reinterpret_cast<float4*> (S.dw);
-#pragma unroll 5
-      for (int j = lane; j < BRICK_NODES / 2; j += 32) s4[j] = g4[j];
-      if (COLOR)
-      {
-        const uint4* gc = reinterpret_cast<const uint4*> (grgb);
-        uint4* sc = reinterpret_cast<uint4*> (S.rgb);
-#pragma unroll 5
-        for (int j = lane; j < BRICK_NODES / 4; j += 32) sc[j] = gc[j];
-      }
+      fence_proxy_async_smem ();                  // earlier generic accesses to this buffer precede the async writes
+      const uint32_t bytes = (uint32_t) sizeof (S.dw) + (COLOR ? (uint32_t) sizeof (S.rgb) : 0u);
+      mbar_expect_tx (&S.bar, bytes);
+      tma_bulk_g2s (S.dw, gdw, (uint32_t) sizeof (S.dw), &S.bar);
+      if (COLOR) tma_bulk_g2s (S.rgb, grgb, (uint32_t) sizeof (S.rgb), &S.bar);
     }
     const uint32_t s1_old = gsw[0] & 0xFFu;
     const uint32_t s2_old0 = gsw[1], s2_old1 = gsw[2];
+    if (!mbar_wait (&S.bar, tma_phase)) { if (lane == 0) raise_err (p, ERR_QUEUE_FULL); break; }
+    tma_phase ^= 1u;
     __syncwarp ();
 
     bool bail_f = false;
