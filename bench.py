@@ -141,13 +141,34 @@ def run_reference(args, rank, world):
     frames_per_step = 4
     from oracle import oracle_py
     kind = "reference" if os.path.exists(oracle_py.REF_LIB) else "port"
-    nt = int(os.environ.get("B200TSDF_REF_THREADS", "0")) or min(nproc, 4)     # 4 threads was the reference's best
-    os.environ["OMP_NUM_THREADS"] = str(nt)
-    v = oracle_volume(kind)
     import ctypes
-    v.cfg.num_threads = nt
-    v.lib.orc_destroy(v.h); v.h = v.lib.orc_create(ctypes.byref(v.cfg))
-    v.reset()
+
+    def make(nt):
+        os.environ["OMP_NUM_THREADS"] = str(nt)
+        v = oracle_volume(kind)
+        v.cfg.num_threads = nt
+        v.lib.orc_destroy(v.h); v.h = v.lib.orc_create(ctypes.byref(v.cfg))
+        v.reset()
+        return v
+
+    # the reference's OpenMP update loop scales poorly: give it the thread count it runs best with
+    nt = int(os.environ.get("B200TSDF_REF_THREADS", "0"))
+    if not nt:
+        best = None
+        for cand in sorted({1, 2, 4, 8, 16, nproc}):
+            if cand > nproc:
+                continue
+            pv = make(cand)
+            pv.integrate(clouds[0], poses[0])
+            t0 = time.perf_counter()
+            for i in (1, 2):
+                pv.integrate(clouds[i], poses[i])
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, cand)
+            del pv
+        nt = best[1]
+    v = make(nt)
     k = 0
     for _ in range(args.warmup):
         for _ in range(frames_per_step):
@@ -186,6 +207,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool-log2", type=int, default=20, help="brick pool capacity = 2^N slots (the bench scene allocates ~37k bricks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,7 +233,7 @@ def main():
         torch.cuda.synchronize()
 
     poses, clouds = make_inputs()
-    vol = pkg.TSDFVolumeOctree(device=local_rank, pool_log2=20, shard_rank=rank, shard_count=world)
+    vol = pkg.TSDFVolumeOctree(device=local_rank, pool_log2=args.pool_log2, shard_rank=rank, shard_count=world)
     vol.setGridSize(SIZE, SIZE, SIZE)
     vol.setResolution(RES, RES, RES)
     vol.setCameraIntrinsics(CAM.fx, CAM.fy, CAM.cx, CAM.cy)

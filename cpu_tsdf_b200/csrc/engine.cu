@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace b2;
@@ -226,6 +227,30 @@ __global__ void k_gather_bricks (Params p, const int* __restrict__ list, int n,
   }
   for (int i = threadIdx.x; i < BRICK_SPLIT_WORDS; i += blockDim.x)
     split[(size_t) b * BRICK_SPLIT_WORDS + i] = p.split[s * BRICK_SPLIT_WORDS + i];
+}
+
+// .vol import: claim each brick's slot and copy its payload in
+__global__ void k_load_bricks (Params p, const uint64_t* __restrict__ keys, int n, const float2* __restrict__ nodes, const uint32_t* __restrict__ split,
+                               const uchar4* __restrict__ rgb, const float* __restrict__ M, const int* __restrict__ ns)
+{
+  __shared__ int slot_s;
+  int b = blockIdx.x;
+  if (b >= n) return;
+  if (threadIdx.x == 0)
+  {
+    uint64_t key = keys[b];
+    slot_s = find_or_insert_brick (p, (int) (key >> 60) - 1, (int) ((key >> 40) & 0xFFFFF), (int) ((key >> 20) & 0xFFFFF), (int) (key & 0xFFFFF));
+  }
+  __syncthreads ();
+  if (slot_s < 0) return;
+  size_t s = (size_t) slot_s;
+  for (int i = threadIdx.x; i < BRICK_NODES; i += blockDim.x)
+  {
+    p.nodes[s * BRICK_NODES + i] = nodes[(size_t) b * BRICK_NODES + i];
+    if (p.rgb && rgb) p.rgb[s * BRICK_NODES + i] = rgb[(size_t) b * BRICK_NODES + i];
+    if (p.M && M) { p.M[s * BRICK_NODES + i] = M[(size_t) b * BRICK_NODES + i]; p.ns[s * BRICK_NODES + i] = ns[(size_t) b * BRICK_NODES + i]; }
+  }
+  for (int i = threadIdx.x; i < BRICK_SPLIT_WORDS; i += blockDim.x) p.split[s * BRICK_SPLIT_WORDS + i] = split[(size_t) b * BRICK_SPLIT_WORDS + i];
 }
 
 // ---- marching cubes: one warp per allocated brick, warp-scan compaction of the triangle soup ----
@@ -1198,4 +1223,130 @@ int b200tsdf_save (b200tsdf_t* h, const char* path)
   return bad ? h->fail (B200TSDF_EIO, "write failed") : B200TSDF_OK;
 }
 
+
+// ---- load (tsdf_volume_octree.cpp:248-275; Octree::deserialize octree.cpp:659-678; OctreeNode::deserialize :306-325) ----
+namespace {
+struct VolLoader
+{
+  std::FILE* f; bool rgb; const Params* p; bool bad = false; std::string why;
+  // host image of the volume being rebuilt
+  std::vector<float2> root_dw; std::vector<uint32_t> root_split; std::vector<uchar4> root_rgb; std::vector<float> root_M; std::vector<int> root_ns;
+  std::vector<uint64_t> keys; std::vector<float2> nodes; std::vector<uint32_t> split; std::vector<uchar4> rgbv; std::vector<float> Mv; std::vector<int> nsv;
+  std::unordered_map<uint64_t, int> index;
+  int brick_of (int t, int x, int y, int z)
+  {
+    uint64_t key = brick_key (t, x, y, z);
+    auto it = index.find (key);
+    if (it != index.end ()) return it->second;
+    index[key] = (int) keys.size ();
+    keys.push_back (key);
+    nodes.resize (keys.size () * BRICK_NODES, make_float2 (-1.f, 0.f));
+    split.resize (keys.size () * BRICK_SPLIT_WORDS, 0u);
+    rgbv.resize (keys.size () * BRICK_NODES, make_uchar4 (0, 0, 0, 0));
+    Mv.resize (keys.size () * BRICK_NODES, 0.f); nsv.resize (keys.size () * BRICK_NODES, 0);
+    return (int) keys.size () - 1;
+  }
+  void node (int level, int x, int y, int z)
+  {
+    if (bad) return;
+    unsigned char c3[3] = { 0, 0, 0 };
+    float v[7]; int nsamp; size_t nchild;
+    bool ok = true;
+    if (rgb) ok = ok && std::fread (c3, 1, 3, f) == 3;
+    ok = ok && std::fread (v, 4, 7, f) == 7 && std::fread (&nsamp, 4, 1, f) == 1 && std::fread (&nchild, sizeof (size_t), 1, f) == 1;
+    if (!ok || (nchild != 0 && nchild != 8)) { bad = true; why = "truncated or malformed node record"; return; }
+    const Params& P = *p;
+    if (level < P.C && nchild != 8) { bad = true; why = "tree is shallower than the coarse depth implied by max_cell_size"; return; }
+    if (level > P.L || (level == P.L && nchild)) { bad = true; why = "tree is deeper than the resolution"; return; }
+    if (level >= P.Rtop)
+    {
+      if (level == P.Rtop)
+      {
+        int ri = root_index (P, x, y, z);
+        root_dw[ri] = make_float2 (v[0], v[1]); root_rgb[ri] = make_uchar4 (c3[0], c3[1], c3[2], 0); root_M[ri] = v[6]; root_ns[ri] = nsamp;
+        if (nchild && level >= P.C) root_split[ri >> 5] |= 1u << (ri & 31);
+      }
+      else
+      {
+        int t = tier_of_level (P, level), k = level - tier_root_level (P, t);
+        int b = brick_of (t, x >> k, y >> k, z >> k);
+        int j = path_index (k, x, y, z), idx = node_offset (k) + j;
+        size_t o = (size_t) b * BRICK_NODES + idx;
+        nodes[o] = make_float2 (v[0], v[1]); rgbv[o] = make_uchar4 (c3[0], c3[1], c3[2], 0); Mv[o] = v[6]; nsv[o] = nsamp;
+        if (nchild && level >= P.C && level < P.L) split[(size_t) b * BRICK_SPLIT_WORDS + split_word_base (k) + (j >> 5)] |= 1u << (j & 31);
+      }
+    }
+    for (size_t c = 0; c < nchild; ++c) node (level + 1, 2 * x + (int) ((c >> 2) & 1), 2 * y + (int) ((c >> 1) & 1), 2 * z + (int) (c & 1));
+  }
+};
+}
+
+int b200tsdf_load (b200tsdf_t* h, const char* path)
+{
+  if (!h || !path) return B200TSDF_EINVAL;
+  std::FILE* f = std::fopen (path, "rb");
+  if (!f) return h->fail (B200TSDF_EIO, std::string ("cannot open ") + path);
+  b200tsdf_config c = h->cfg_pending;
+  char line[1024];
+  auto fail = [&] (const std::string& m) { std::fclose (f); return h->fail (B200TSDF_EIO, std::string (path) + ": " + m); };
+  if (!std::fgets (line, sizeof (line), f)) return fail ("empty file");
+  int is_empty = 0, wd = 0, wv = 0;
+  double gt[16];
+  int nread = std::fscanf (f, "%d %d %d %f %f %f %f %f %f %f %f %f %f %f %lf %lf %lf %lf %d %d %d %d %d",
+                           &c.xres, &c.yres, &c.zres, &c.xsize, &c.ysize, &c.zsize, &c.max_dist_pos, &c.max_dist_neg, &c.max_weight,
+                           &c.min_sensor_dist, &c.max_sensor_dist, &c.max_cell_x, &c.max_cell_y, &c.max_cell_z,
+                           &c.fx, &c.fy, &c.cx, &c.cy, &c.image_width, &c.image_height, &is_empty, &wd, &wv);
+  if (nread != 23) return fail ("bad header");
+  char pct[8]; int rr = 0, cc = 0;
+  if (std::fscanf (f, " %1s %d %d", pct, &rr, &cc) != 3 || pct[0] != '%' || rr != 4 || cc != 4) return fail ("bad transform header");
+  for (int i = 0; i < 16; ++i) if (std::fscanf (f, "%lf", &gt[i]) != 1) return fail ("bad transform");
+  char type[64];
+  if (std::fscanf (f, "%63s", type) != 1) return fail ("missing node type");
+  bool rgb = std::string (type) == "RGB";
+  if (!rgb && std::string (type) != "NOCOLOR") return fail (std::string ("unsupported node type ") + type);
+  do { if (!std::fgets (line, sizeof (line), f)) return fail ("missing #OCTREEBINARY"); } while (!(line[0] == '#' && line[1] == 'O'));
+  size_t res3[3]; float size3[3];
+  if (std::fread (res3, sizeof (size_t), 3, f) != 3 || std::fread (size3, 4, 3, f) != 3) return fail ("truncated octree header");
+  c.integrate_color = rgb ? 1 : 0;
+  for (int i = 0; i < 16; ++i) c.global_transform[i] = gt[i];
+  h->cfg_pending = c;
+  int rc = b200tsdf_reset (h);
+  if (rc) { std::fclose (f); return rc; }
+  const Params& p = h->p;
+  VolLoader L; L.f = f; L.rgb = rgb; L.p = &p;
+  size_t rn = h->root_n;
+  L.root_dw.assign (rn, make_float2 (-1.f, 0.f)); L.root_split.assign ((rn + 31) / 32, 0u);
+  L.root_rgb.assign (rn, make_uchar4 (0, 0, 0, 0)); L.root_M.assign (rn, 0.f); L.root_ns.assign (rn, 0);
+  L.node (0, 0, 0, 0);
+  std::fclose (f);
+  if (L.bad) return h->fail (B200TSDF_EIO, std::string (path) + ": " + L.why);
+  cudaSetDevice (h->device);
+  CK (cudaMemcpy (p.root_dw, L.root_dw.data (), rn * sizeof (float2), cudaMemcpyHostToDevice));
+  CK (cudaMemcpy (p.root_split, L.root_split.data (), L.root_split.size () * sizeof (uint32_t), cudaMemcpyHostToDevice));
+  if (p.root_rgb) CK (cudaMemcpy (p.root_rgb, L.root_rgb.data (), rn * sizeof (uchar4), cudaMemcpyHostToDevice));
+  if (p.root_M) { CK (cudaMemcpy (p.root_M, L.root_M.data (), rn * sizeof (float), cudaMemcpyHostToDevice)); CK (cudaMemcpy (p.root_ns, L.root_ns.data (), rn * sizeof (int), cudaMemcpyHostToDevice)); }
+  int nb = (int) L.keys.size ();
+  if (nb)
+  {
+    uint64_t* dk = nullptr; float2* dn = nullptr; uint32_t* ds = nullptr; uchar4* dc = nullptr; float* dM = nullptr; int* dns = nullptr;
+    CK (cudaMalloc (&dk, (size_t) nb * 8)); CK (cudaMalloc (&dn, (size_t) nb * BRICK_NODES * sizeof (float2))); CK (cudaMalloc (&ds, (size_t) nb * BRICK_SPLIT_WORDS * 4));
+    CK (cudaMemcpy (dk, L.keys.data (), (size_t) nb * 8, cudaMemcpyHostToDevice));
+    CK (cudaMemcpy (dn, L.nodes.data (), (size_t) nb * BRICK_NODES * sizeof (float2), cudaMemcpyHostToDevice));
+    CK (cudaMemcpy (ds, L.split.data (), (size_t) nb * BRICK_SPLIT_WORDS * 4, cudaMemcpyHostToDevice));
+    if (p.rgb) { CK (cudaMalloc (&dc, (size_t) nb * BRICK_NODES * 4)); CK (cudaMemcpy (dc, L.rgbv.data (), (size_t) nb * BRICK_NODES * 4, cudaMemcpyHostToDevice)); }
+    if (p.M)
+    {
+      CK (cudaMalloc (&dM, (size_t) nb * BRICK_NODES * 4)); CK (cudaMalloc (&dns, (size_t) nb * BRICK_NODES * 4));
+      CK (cudaMemcpy (dM, L.Mv.data (), (size_t) nb * BRICK_NODES * 4, cudaMemcpyHostToDevice));
+      CK (cudaMemcpy (dns, L.nsv.data (), (size_t) nb * BRICK_NODES * 4, cudaMemcpyHostToDevice));
+    }
+    k_load_bricks<<<nb, 128, 0, h->stream>>> (p, dk, nb, dn, ds, dc, dM, dns);
+    CK (cudaStreamSynchronize (h->stream));
+    cudaFree (dk); cudaFree (dn); cudaFree (ds); cudaFree (dc); cudaFree (dM); cudaFree (dns);
+  }
+  h->is_empty = is_empty != 0;
+  return check_device_err (h);
+}
+
 } // extern "C"
+

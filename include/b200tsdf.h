@@ -111,6 +111,12 @@ void b200tsdf_free (void* p);
 /* TSDFVolumeOctree::save (cpp:222-245): reference-compatible .vol */
 int  b200tsdf_save (b200tsdf_t* h, const char* path);
 
+/* TSDFVolumeOctree::load (cpp:248-275) / TSDFInterface::instantiateFromFile (src/lib/tsdf_interface.cpp:44-51):
+ * reads a reference-format .vol (written by the reference or by b200tsdf_save), adopts its configuration
+ * (resolution, size, truncation, intrinsics, ..., colour node type) and rebuilds the volume on the device.
+ * OctreeNode::M_/nsample_ are kept only if track_variance was set on the handle. */
+int  b200tsdf_load (b200tsdf_t* h, const char* path);
+
 /* getVoxelCenter / getVoxelIndex (cpp:553-574) */
 int  b200tsdf_voxel_center (const b200tsdf_t* h, int64_t x, int64_t y, int64_t z, float* out3);
 int  b200tsdf_voxel_index (const b200tsdf_t* h, float x, float y, float z, int32_t* out3, int32_t* inside);

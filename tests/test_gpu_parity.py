@@ -235,3 +235,25 @@ def test_sharded_volumes_union_is_the_whole_volume():
         assert np.array_equal(d["keys"][own], ref["keys"][owner == r])
         assert np.array_equal(d["dw"][own].view(np.uint32), ref["dw"][owner == r].view(np.uint32))
         assert (d["dw"][~own] == [-1, 0]).all() and not d["split"][~own].any()
+
+
+def test_load_vol_written_by_the_reference_path(tmp_path):
+    # TSDFVolumeOctree::load (cpp:248-275): import a .vol written by the oracle, continue fusing, and stay exact
+    o, e = pair(CFG_256, integrate_color=1, track_variance=1)
+    fr = list(frames(synth.S1, 4, stride=7, color=True, noise_seed=5))
+    for pose, cloud in fr[:2]:
+        o.integrate(cloud, pose)
+    pa = str(tmp_path / "a.vol")
+    assert o.save(pa) == 0
+    v = pkg.TSDFVolumeOctree(device=0, pool_log2=17, track_variance=True)
+    v.load(pa)
+    assert v.getResolution() == (256, 256, 256) and v.getCameraIntrinsics()[2] == CAM.cx
+    assert_same_nodes(o.dump_nodes(), v.download_nodes(), rgb=True, var=True)
+    for pose, cloud in fr[2:]:
+        o.integrate(cloud, pose); v.integrateCloud(cloud, None, pose)
+    assert_same_nodes(o.dump_nodes(), v.download_nodes(), rgb=True, var=True)
+    pb = str(tmp_path / "b.vol")
+    v.save(pb); o.save(pa)
+    assert open(pa, "rb").read() == open(pb, "rb").read()
+    with pytest.raises(pkg.B200Error):
+        v.load(str(tmp_path / "missing.vol"))
