@@ -817,4 +817,337 @@ __global__ void k_bail (Params p, Frame f, Queues Q, int li, const int* __restri
   }
 }
 
+
+// ---- 1c/3c. upper sweeps for the common shape: coarse cell == root of a tier-1 brick, block roots 3 levels below ----
+// k_celltop_down: one CTA per culled coarse cell.  All 585 nodes of the cell's upper pyramid (cell + 8 + 64 + 512
+// block roots) are OBSERVED SPECULATIVELY in parallel (observation is a pure function of geometry and frame) while
+// the tier-1 brick is staged into shared memory, so the level-by-level decisions run from shared memory instead
+// of a chain of dependent DRAM loads.  Interior block roots are queued for k_blocks exactly as before.
+// k_celltop_up: one WARP per cell folds the return codes with ballots (the bottom-up half of k_blocks, operating on
+// the brick in global memory: only pruned nodes are touched).
+constexpr int TOP_THREADS = 256;
+constexpr int TOP_NODES = 585;                       // flat index f: 0 = cell, 1..8, 9..72, 73..584
+struct CellTop                                       // per-cell scratch between the two sweeps
+{
+  int t1slot, nblk;
+  unsigned char kind[592];
+  signed char rc[592];
+  float dnew[73];
+  int uv[73];
+};
+struct TopSmem
+{
+  float2 dw[BRICK_NODES];
+  uchar4 rgb[BRICK_NODES];
+  float o_dnew[TOP_NODES];
+  int o_uv[TOP_NODES];
+  uint32_t o_bgra[TOP_NODES];
+  unsigned char o_flags[592];                        // bit0 valid, bit1 near
+  unsigned char kind[592];
+  signed char rc[592];
+  unsigned char dirty[592];
+  uint32_t split[BRICK_SPLIT_WORDS];
+  uint32_t split_old[BRICK_SPLIT_WORDS];
+  QNode cell;
+  int t1slot, root_interior;
+  float c0[3];
+};
+
+__device__ __forceinline__ void top_kj (int f, int& k, int& j)
+{ if (f == 0) { k = 0; j = 0; } else if (f < 9) { k = 1; j = f - 1; } else if (f < 73) { k = 2; j = f - 9; } else { k = 3; j = f - 73; } }
+
+template <bool COLOR>
+__global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, Frame f, const QNode* __restrict__ cells, const int* __restrict__ ncells,
+                                                               QNode* __restrict__ gq, CellTop* __restrict__ tops, int cell_cap,
+                                                               int* __restrict__ blist, int* __restrict__ bcount, unsigned long long* __restrict__ stats)
+{
+  __shared__ __align__ (16) TopSmem S;
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned long long upd = 0, vis = 0;
+  int count = *ncells;
+  if (count > cell_cap) { if (tid == 0 && blockIdx.x == 0) raise_err (p, ERR_QUEUE_FULL); count = cell_cap; }
+  const float sizeC = level_size (p, p.C);
+  const float off1 = sizeC * 0.25f;
+  const double thr[4] = { near_threshold (sizeC), near_threshold (sizeC * 0.5f), near_threshold (sizeC * 0.25f), near_threshold (sizeC * 0.125f) };
+  for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
+  {
+    __syncthreads ();
+    if (tid == 0)
+    {
+      S.cell = cells[ci];
+      S.c0[0] = center1d (p, p.C, S.cell.x); S.c0[1] = center1d (p, p.C, S.cell.y); S.c0[2] = center1d (p, p.C, S.cell.z);
+    }
+    __syncthreads ();
+    const QNode cell = S.cell;
+    const float c0[3] = { S.c0[0], S.c0[1], S.c0[2] };
+    // ---- speculative observation of every node (independent loads, issued before anything else is waited on) ----
+    for (int n = tid; n < TOP_NODES; n += TOP_THREADS)
+    {
+      int k, j; top_kj (n, k, j);
+      float c[3];
+      if (k == 0) { c[0] = c0[0]; c[1] = c0[1]; c[2] = c0[2]; } else path_center (c0, off1, k, j, c);
+      Obs o = observe_thr (p, f, c[0], c[1], c[2], thr[k]);
+      S.o_dnew[n] = o.d_new; S.o_uv[n] = o.u | (o.v << 16);
+      S.o_bgra[n] = (COLOR && o.valid && f.rgba_off >= 0) ? *reinterpret_cast<const uint32_t*> (frame_bgr (f, o.u, o.v)) : 0u;
+      S.o_flags[n] = (unsigned char) ((o.valid ? 1 : 0) | (o.near_ ? 2 : 0));
+      S.kind[n] = KIND_DONE; S.rc[n] = 0; S.dirty[n] = 0;
+    }
+    // ---- the cell itself (root arrays) ----
+    if (tid == 0)
+    {
+      NodePos nc; nc.level = p.C; nc.x = cell.x; nc.y = cell.y; nc.z = cell.z; nc.cx = c0[0]; nc.cy = c0[1]; nc.cz = c0[2]; nc.size = sizeC; nc.slot = -1; nc.idx = cell.idx;
+      uint32_t m; uint32_t* sw = split_word (p, nc, m);
+      int kind = KIND_DONE, rc = 0, slot = -1;
+      vis++;
+      if (*sw & m) { kind = KIND_OLD; slot = find_brick (p, p.T - 1, cell.x, cell.y, cell.z); if (slot < 0) { raise_err (p, ERR_MISSING_BRICK); kind = KIND_DONE; } }
+      else
+      {
+        Obs o = observe_thr (p, f, c0[0], c0[1], c0[2], thr[0]);
+        if (o.valid)
+        {
+          if (o.near_) { slot = find_or_insert_brick (p, p.T - 1, cell.x, cell.y, cell.z); if (slot >= 0) { kind = KIND_NEW; atomicOr (sw, m); } }
+          else { bool u_; rc = leaf_update (p, f, nc, o, u_); upd += u_; }
+        }
+      }
+      S.root_interior = kind; S.t1slot = slot;
+      S.kind[0] = (unsigned char) kind; S.rc[0] = (signed char) rc;     // (written after the init loop of this thread: n = 0 is tid 0's)
+    }
+    __syncthreads ();
+    const int t1 = S.t1slot;
+    CellTop* top = tops + ci;
+    if (S.root_interior == KIND_DONE)
+    {
+      if (tid == 0) { top->t1slot = -1; top->nblk = 0; top->kind[0] = KIND_DONE; top->rc[0] = S.rc[0]; }
+      continue;
+    }
+    // ---- stage the tier-1 brick ----
+    float2* gdw = p.nodes + (size_t) t1 * BRICK_NODES;
+    uchar4* grgb = COLOR ? p.rgb + (size_t) t1 * BRICK_NODES : nullptr;
+    uint32_t* gsw = p.split + (size_t) t1 * BRICK_SPLIT_WORDS;
+    {
+      const float4* g4 = reinterpret_cast<const float4*> (gdw);
+      float4* s4 = reinterpret_cast<float4*> (S.dw);
+      for (int i = tid; i < BRICK_NODES / 2; i += TOP_THREADS) s4[i] = g4[i];
+      if (COLOR)
+      {
+        const uint4* gc = reinterpret_cast<const uint4*> (grgb);
+        uint4* sc = reinterpret_cast<uint4*> (S.rgb);
+        for (int i = tid; i < BRICK_NODES / 4; i += TOP_THREADS) sc[i] = gc[i];
+      }
+      if (tid < BRICK_SPLIT_WORDS) { uint32_t w = gsw[tid]; S.split[tid] = w; S.split_old[tid] = w; }
+    }
+    __syncthreads ();
+    // ---- level by level from shared memory ----
+    for (int k = 1; k <= 3; ++k)
+    {
+      const int nlev = 1 << (3 * k), base = (k == 1) ? 1 : (k == 2 ? 9 : 73), pbase = (k == 1) ? 0 : (k == 2 ? 1 : 9);
+      for (int j = tid; j < nlev; j += TOP_THREADS)
+      {
+        const int n = base + j;
+        if (S.kind[pbase + (j >> 3)] == KIND_DONE) continue;          // parent is not interior: node not visited
+        vis++;
+        const bool sold = (S.split_old[split_word_base (k) + (j >> 5)] >> (j & 31)) & 1;
+        int kind = KIND_DONE, rc = 0;
+        if (sold) kind = KIND_OLD;
+        else if (S.o_flags[n] & 1)
+        {
+          if (S.o_flags[n] & 2) { kind = KIND_NEW; atomicOr (&S.split[split_word_base (k) + (j >> 5)], 1u << (j & 31)); }
+          else
+          {
+            const int si = n - 1;                                  // in-brick node index
+            float M = 0.f; int ns = 0; bool u_;
+            const bool have = COLOR && f.rgba_off >= 0;
+            rc = leaf_update_core (p, S.o_dnew[n], have, S.o_bgra[n], S.dw[si], S.rgb[si], M, ns, u_);
+            if (u_) { S.dirty[n] = 1; upd++; }
+          }
+        }
+        S.kind[n] = (unsigned char) kind; S.rc[n] = (signed char) rc;
+      }
+      __syncthreads ();
+    }
+    // ---- interior block roots -> block list (+ their QNode for k_blocks) ----
+    constexpr int STRIDE = 585;
+    for (int base = 0; base < 512; base += TOP_THREADS)
+    {
+      const int j3 = base + tid, n = 73 + j3;
+      const int kind = S.kind[n];
+      const bool interior = kind != KIND_DONE;
+      int bslot = -1;
+      if (interior)
+      {
+        int lx = 0, ly = 0, lz = 0;
+        for (int q = 2; q >= 0; --q) { int c = (j3 >> (3 * q)) & 7; lx = (lx << 1) | (c >> 2); ly = (ly << 1) | ((c >> 1) & 1); lz = (lz << 1) | (c & 1); }
+        const int X = (cell.x << 3) | lx, Y = (cell.y << 3) | ly, Z = (cell.z << 3) | lz;
+        bslot = (kind == KIND_OLD) ? find_brick (p, 0, X, Y, Z) : find_or_insert_brick (p, 0, X, Y, Z);
+        if (bslot < 0) { if (kind == KIND_OLD) raise_err (p, ERR_MISSING_BRICK); }
+        QNode e; e.x = X; e.y = Y; e.z = Z; e.slot = t1; e.idx = 72 + j3; e.kind = kind; e.child_base = bslot; e.rc = 0;
+        gq[(size_t) ci * STRIDE + 73 + j3] = e;
+      }
+      const bool push = interior && bslot >= 0;
+      const unsigned mask = __ballot_sync (0xffffffffu, push);
+      if (mask)
+      {
+        int b = 0;
+        const int leader = __ffs (mask) - 1;
+        if (lane == leader) b = atomicAdd (bcount, __popc (mask));
+        b = __shfl_sync (0xffffffffu, b, leader);
+        if (push) blist[b + __popc (mask & ((1u << lane) - 1))] = ci * STRIDE + 73 + j3;
+      }
+    }
+    // ---- write back what changed, and the scratch for the bottom-up sweep ----
+    for (int n = 1 + tid; n < TOP_NODES; n += TOP_THREADS)
+      if (S.dirty[n]) { gdw[n - 1] = S.dw[n - 1]; if (COLOR) grgb[n - 1] = S.rgb[n - 1]; }
+    if (tid < BRICK_SPLIT_WORDS && S.split[tid] != S.split_old[tid]) gsw[tid] = S.split[tid];
+    for (int n = tid; n < 592; n += TOP_THREADS) { top->kind[n] = n < TOP_NODES ? S.kind[n] : 0; top->rc[n] = n < TOP_NODES ? S.rc[n] : 0; }
+    for (int n = tid; n < 73; n += TOP_THREADS) { top->dnew[n] = S.o_dnew[n]; top->uv[n] = S.o_uv[n]; }
+    if (tid == 0) { top->t1slot = t1; top->nblk = 0; }
+  }
+  __syncwarp ();
+  warp_add_stats (stats, upd, vis);
+}
+
+// fall-through update (hpp:189-214) of an upper node whose children were all pruned; state in GLOBAL memory
+__device__ __forceinline__ int top_fallthrough_new (const Params& p, const Frame& f, const NodePos& n, float dnew, int uv, unsigned long long& upd)
+{
+  Obs o; o.valid = true; o.near_ = true; o.d_new = dnew; o.u = uv & 0xFFFF; o.v = uv >> 16;
+  bool u_; int rc = leaf_update (p, f, n, o, u_); upd += u_;
+  return rc;
+}
+
+template <bool COLOR>
+__global__ void __launch_bounds__ (128) k_celltop_up (Params p, Frame f, const QNode* __restrict__ cells, const int* __restrict__ ncells,
+                                                      const QNode* __restrict__ gq, const CellTop* __restrict__ tops, int cell_cap,
+                                                      unsigned long long* __restrict__ stats)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long upd = 0, vis = 0;
+  int count = *ncells;
+  if (count > cell_cap) count = cell_cap;
+  const float sizeC = level_size (p, p.C);
+  const float off1 = sizeC * 0.25f;
+  constexpr int STRIDE = 585;
+  for (int ci = warp; ci < count; ci += nwarps)
+  {
+    const CellTop* top = tops + ci;
+    const int t1 = top->t1slot;
+    if (t1 < 0) continue;                                            // the cell was a leaf: nothing to fold
+    const QNode cell = cells[ci];
+    const float c0[3] = { center1d (p, p.C, cell.x), center1d (p, p.C, cell.y), center1d (p, p.C, cell.z) };
+    float2* gdw = p.nodes + (size_t) t1 * BRICK_NODES;
+    uchar4* grgb = COLOR ? p.rgb + (size_t) t1 * BRICK_NODES : nullptr;
+    uint32_t* gsw = p.split + (size_t) t1 * BRICK_SPLIT_WORDS;
+    // ---- level 3 (block roots): "rc >= 0" ballots, j3 = lane + 32 i ----
+    const int kind1 = lane < 8 ? top->kind[1 + lane] : KIND_DONE;
+    int kind2[2]; kind2[0] = top->kind[9 + lane]; kind2[1] = top->kind[9 + 32 + lane];
+    const uint32_t int1 = __ballot_sync (0xffffffffu, kind1 != KIND_DONE);
+    uint32_t int2[2]; int2[0] = __ballot_sync (0xffffffffu, kind2[0] != KIND_DONE); int2[1] = __ballot_sync (0xffffffffu, kind2[1] != KIND_DONE);
+    uint32_t nonneg_mine = 0;
+    {
+      // all loads first (16 independent kind/rc bytes per lane, then the interior block roots' return codes)
+      int k3[16], r3[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { k3[i] = top->kind[73 + lane + 32 * i]; r3[i] = top->rc[73 + lane + 32 * i]; }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (k3[i] != KIND_DONE) r3[i] = gq[(size_t) ci * STRIDE + 73 + lane + 32 * i].rc;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+      {
+        const int j2 = (lane + 32 * i) >> 3;
+        const bool visited = ((j2 < 32 ? int2[0] : int2[1]) >> (j2 & 31)) & 1;
+        const uint32_t nn = __ballot_sync (0xffffffffu, visited && r3[i] >= 0);
+        if (lane == i) nonneg_mine = nn;
+      }
+    }
+    // ---- level 2 ----
+    uint32_t nonneg2[2];
+#pragma unroll
+    for (int i2 = 0; i2 < 2; ++i2)
+    {
+      const int j2 = lane + 32 * i2;
+      const uint32_t nn = __shfl_sync (0xffffffffu, nonneg_mine, (lane >> 2) + 8 * i2);
+      int rc = top->rc[9 + j2];
+      bool slow = false;
+      NodePos n;
+      if (kind2[i2] != KIND_DONE)
+      {
+        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc = 1;
+        else
+        {
+          // prune: children.clear () -> split bit off, eight block-root nodes back to the fresh state
+          atomicAnd (&gsw[1 + (j2 >> 5)], ~(1u << (j2 & 31)));
+          for (int c = 0; c < 8; ++c) { gdw[72 + 8 * j2 + c] = make_float2 (-1.f, 0.f); if (COLOR) grgb[72 + 8 * j2 + c] = make_uchar4 (0, 0, 0, 0); }
+          float c[3]; path_center (c0, off1, 2, j2, c);
+          n.level = p.C + 2; n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.25f; n.slot = t1; n.idx = 8 + j2;
+          { int lx = 0, ly = 0, lz = 0; for (int q = 1; q >= 0; --q) { int cc = (j2 >> (3 * q)) & 7; lx = (lx << 1) | (cc >> 2); ly = (ly << 1) | ((cc >> 1) & 1); lz = (lz << 1) | (cc & 1); }
+            n.x = (cell.x << 2) | lx; n.y = (cell.y << 2) | ly; n.z = (cell.z << 2) | lz; }
+          if (kind2[i2] == KIND_NEW) rc = top_fallthrough_new (p, f, n, top->dnew[9 + j2], top->uv[9 + j2], upd);
+          else slow = true;
+        }
+      }
+      // pre-existing children pruned: leaf visit by the whole warp, one node at a time (rare)
+      uint32_t sm = __ballot_sync (0xffffffffu, slow);
+      while (sm)
+      {
+        const int src = __ffs (sm) - 1; sm &= sm - 1;
+        NodePos q;
+        q.level = __shfl_sync (0xffffffffu, n.level, src); q.x = __shfl_sync (0xffffffffu, n.x, src); q.y = __shfl_sync (0xffffffffu, n.y, src); q.z = __shfl_sync (0xffffffffu, n.z, src);
+        q.cx = __shfl_sync (0xffffffffu, n.cx, src); q.cy = __shfl_sync (0xffffffffu, n.cy, src); q.cz = __shfl_sync (0xffffffffu, n.cz, src);
+        q.size = __shfl_sync (0xffffffffu, n.size, src); q.slot = t1; q.idx = __shfl_sync (0xffffffffu, n.idx, src);
+        __threadfence_block ();
+        int r = leaf_visit_warp8 (p, f, q, upd, vis);
+        if (lane == src) rc = r;
+      }
+      const bool visited2 = (int1 >> (j2 >> 3)) & 1;
+      nonneg2[i2] = __ballot_sync (0xffffffffu, visited2 && rc >= 0);
+    }
+    // ---- level 1 ----
+    int rc1 = lane < 8 ? (int) top->rc[1 + lane] : 0;
+    {
+      bool slow = false;
+      NodePos n;
+      if (lane < 8 && kind1 != KIND_DONE)
+      {
+        const uint32_t nn = nonneg2[lane >> 2];
+        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc1 = 1;
+        else
+        {
+          atomicAnd (&gsw[0], ~(1u << lane));
+          for (int c = 0; c < 8; ++c) { gdw[8 + 8 * lane + c] = make_float2 (-1.f, 0.f); if (COLOR) grgb[8 + 8 * lane + c] = make_uchar4 (0, 0, 0, 0); }
+          float c[3]; path_center (c0, off1, 1, lane, c);
+          n.level = p.C + 1; n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.5f; n.slot = t1; n.idx = lane;
+          n.x = (cell.x << 1) | ((lane >> 2) & 1); n.y = (cell.y << 1) | ((lane >> 1) & 1); n.z = (cell.z << 1) | (lane & 1);
+          if (kind1 == KIND_NEW) rc1 = top_fallthrough_new (p, f, n, top->dnew[1 + lane], top->uv[1 + lane], upd);
+          else slow = true;
+        }
+      }
+      uint32_t sm = __ballot_sync (0xffffffffu, slow);
+      while (sm)
+      {
+        const int src = __ffs (sm) - 1; sm &= sm - 1;
+        NodePos q;
+        q.level = __shfl_sync (0xffffffffu, n.level, src); q.x = __shfl_sync (0xffffffffu, n.x, src); q.y = __shfl_sync (0xffffffffu, n.y, src); q.z = __shfl_sync (0xffffffffu, n.z, src);
+        q.cx = __shfl_sync (0xffffffffu, n.cx, src); q.cy = __shfl_sync (0xffffffffu, n.cy, src); q.cz = __shfl_sync (0xffffffffu, n.cz, src);
+        q.size = __shfl_sync (0xffffffffu, n.size, src); q.slot = t1; q.idx = __shfl_sync (0xffffffffu, n.idx, src);
+        __threadfence_block ();
+        int r = leaf_visit_warp8 (p, f, q, upd, vis);
+        if (lane == src) rc1 = r;
+      }
+    }
+    const uint32_t nonneg1 = __ballot_sync (0xffffffffu, lane < 8 && rc1 >= 0);
+    // ---- the cell ----
+    if ((nonneg1 & 0xFFu) == 0)
+    {
+      NodePos nc; nc.level = p.C; nc.x = cell.x; nc.y = cell.y; nc.z = cell.z; nc.cx = c0[0]; nc.cy = c0[1]; nc.cz = c0[2]; nc.size = sizeC; nc.slot = -1; nc.idx = cell.idx;
+      if (lane == 0) { uint32_t m; uint32_t* sw = split_word (p, nc, m); atomicAnd (sw, ~m); }
+      if (lane < 8) { gdw[lane] = make_float2 (-1.f, 0.f); if (COLOR) grgb[lane] = make_uchar4 (0, 0, 0, 0); }
+      __syncwarp ();
+      if (top->kind[0] == KIND_NEW) { if (lane == 0) top_fallthrough_new (p, f, nc, top->dnew[0], top->uv[0], upd); }
+      else { __threadfence_block (); leaf_visit_warp8 (p, f, nc, upd, vis); }
+    }
+  }
+  __syncwarp ();
+  warp_add_stats (stats, upd, vis);
+}
+
 } // namespace b2

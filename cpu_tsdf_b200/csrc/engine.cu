@@ -368,7 +368,7 @@ struct b200tsdf
   Queues Q{}; int q_levels = 0; QNode* q_mem = nullptr; size_t q_mem_cap = 0;
   int* d_blist = nullptr; int* d_bail = nullptr; size_t blist_cap = 0;
   // fused per-cell upper sweeps (coarse cells are the top-tier roots and the block roots are <= 3 levels below)
-  bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0;
+  bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0; CellTop* d_celltop = nullptr; bool top_path = false;
   bool fast_path = false; int force_general = 0;
   // measurement
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
@@ -472,7 +472,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
   free_volume (h);
   cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled);
-  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec);
+  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
   if (h->ev_k0) cudaEventDestroy (h->ev_k0); if (h->ev_k1) cudaEventDestroy (h->ev_k1);
@@ -572,12 +572,14 @@ int b200tsdf_reset (b200tsdf_t* h)
       size_t need = (size_t) h->cell_cap * stride;
       if (need > h->cellq_cap)
       {
-        cudaFree (h->d_cellq); cudaFree (h->d_cellrec); h->d_cellq = nullptr; h->d_cellrec = nullptr; h->cellq_cap = 0;
+        cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop); h->d_cellq = nullptr; h->d_cellrec = nullptr; h->d_celltop = nullptr; h->cellq_cap = 0;
         CK (cudaMalloc (&h->d_cellq, need * sizeof (QNode)));
         CK (cudaMalloc (&h->d_cellrec, (size_t) h->cell_cap * sizeof (CellRecord)));
+        CK (cudaMalloc (&h->d_celltop, (size_t) h->cell_cap * sizeof (CellTop)));
         h->cellq_cap = need;
       }
     }
+    h->top_path = h->cell_path && h->cell_nl == 3 && !(c.reserved[0] & 4);
     size_t bl = h->q_levels ? caps[h->q_levels - 1] : 0;
     if (h->cell_path) bl = std::max (bl, (size_t) h->cell_cap * 512);
     if (bl > h->blist_cap)
@@ -653,7 +655,12 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
       const int NL = h->cell_nl;
       Qb.q[NL] = h->d_cellq; Qb.cap[NL] = (int) std::min (h->cellq_cap, (size_t) 0x7fffffff);
       bli = NL;
-      if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      if (h->top_path)
+      {
+        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      }
+      else if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       else k_cell_down<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       h->launches++;
@@ -661,16 +668,21 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
     else
       for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
     CK (cudaEventRecord (h->kring[kr][0], s));
-    int* bail_list = h->cell_path ? nullptr : h->d_bail;       // the per-cell bottom-up sweep redoes deferred block roots itself
+    int* bail_list = (h->cell_path && !h->top_path) ? nullptr : h->d_bail;   // the generic per-cell bottom-up sweep redoes deferred block roots itself
     if (p.color) k_blocks<true><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, h->d_count + 11, h->d_stats);
     else k_blocks<false><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, h->d_count + 11, h->d_stats);
     CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
-    if (!h->cell_path) { k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats); h->launches++; }
+    if (!h->cell_path || h->top_path) { k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats); h->launches++; }
     if (h->cell_path)
     {
       const int NL = h->cell_nl;
-      if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      if (h->top_path)
+      {
+        if (p.color) k_celltop_up<true><<<h->sm_count * 4, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        else k_celltop_up<false><<<h->sm_count * 4, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+      }
+      else if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
       else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
       else k_cell_up<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
       h->launches++;

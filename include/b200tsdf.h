@@ -50,7 +50,7 @@ typedef struct b200tsdf_config
   int32_t device;                           /* CUDA device ordinal                                */
   int32_t pool_log2;                        /* brick pool capacity = 2^pool_log2 (0 = default 20) */
   int32_t shard_rank, shard_count;          /* this handle owns coarse cells with hash(cell) % shard_count == shard_rank */
-  int32_t reserved[4];                      /* [0] debug — bit0: general depth-first update kernel only; bit1: per-level upper sweeps instead of the fused per-cell ones */
+  int32_t reserved[4];                      /* [0] debug — bit0: general depth-first update kernel only; bit1: per-level upper sweeps instead of the fused per-cell ones; bit2: generic per-cell sweeps instead of the speculative tier-1 ones */
   double  global_transform[16];             /* setGlobalTransform tsdf_volume_octree.h:119; row-major 4x4 */
 } b200tsdf_config;
 
