@@ -1015,10 +1015,23 @@ __device__ __forceinline__ int top_fallthrough_new (const Params& p, const Frame
 }
 
 template <bool COLOR>
-__global__ void __launch_bounds__ (128) k_celltop_up (Params p, Frame f, const QNode* __restrict__ cells, const int* __restrict__ ncells,
+__global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const QNode* __restrict__ cells, const int* __restrict__ ncells,
                                                       const QNode* __restrict__ gq, const CellTop* __restrict__ tops, int cell_cap,
                                                       unsigned long long* __restrict__ stats)
 {
+  // Params / Frame live in shared memory here: the out-of-line slow path takes them by reference, which
+  // would otherwise make every thread copy the kernel parameters to its stack in the prologue
+  __shared__ Params sp_;
+  __shared__ Frame sf_;
+  {
+    const int* s1 = reinterpret_cast<const int*> (&gp); int* d1 = reinterpret_cast<int*> (&sp_);
+    for (int w = threadIdx.x; w < (int) (sizeof (Params) / sizeof (int)); w += blockDim.x) d1[w] = s1[w];
+    const int* s2 = reinterpret_cast<const int*> (&gf); int* d2 = reinterpret_cast<int*> (&sf_);
+    for (int w = threadIdx.x; w < (int) (sizeof (Frame) / sizeof (int)); w += blockDim.x) d2[w] = s2[w];
+  }
+  __syncthreads ();
+  const Params& p = sp_;
+  const Frame& f = sf_;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   unsigned long long upd = 0, vis = 0;

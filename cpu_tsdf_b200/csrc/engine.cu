@@ -679,8 +679,8 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
       const int NL = h->cell_nl;
       if (h->top_path)
       {
-        if (p.color) k_celltop_up<true><<<h->sm_count * 4, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
-        else k_celltop_up<false><<<h->sm_count * 4, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        if (p.color) k_celltop_up<true><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        else k_celltop_up<false><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
       }
       else if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
       else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
