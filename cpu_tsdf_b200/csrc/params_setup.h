@@ -50,7 +50,6 @@ inline const char* derive_params (const b200tsdf_config& c, Params& p, size_t& p
   p.color = c.integrate_color != 0; p.track_var = c.track_variance != 0;
   p.shard_rank = c.shard_rank; p.shard_count = c.shard_count;
   p.pool_mask = (uint32_t) (pool - 1);
-  { const char* dbg = std::getenv ("B200TSDF_DEBUG"); p.debug = dbg ? std::atoi (dbg) : 0; }
   return nullptr;
 }
 

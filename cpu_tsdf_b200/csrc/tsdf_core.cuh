@@ -138,7 +138,6 @@ struct Params
   int color, track_var;
   // sharding: this device owns coarse cells with cell_hash % shard_count == shard_rank
   int shard_rank, shard_count;
-  int debug;                  // experiment switches (B200TSDF_DEBUG); 0 in normal operation
   // storage
   uint64_t* keys;             // [pool]
   uint32_t pool_mask;

@@ -257,3 +257,61 @@ def test_load_vol_written_by_the_reference_path(tmp_path):
     assert open(pa, "rb").read() == open(pb, "rb").read()
     with pytest.raises(pkg.B200Error):
         v.load(str(tmp_path / "missing.vol"))
+
+
+def _engine_2048(general=False, pool_log2=18):
+    v = pkg.TSDFVolumeOctree(device=0, pool_log2=pool_log2)
+    v.setResolution(2048, 2048, 2048); v.setGridSize(10.0, 10.0, 10.0)
+    v.setCameraIntrinsics(525.0, 525.0, CAM.cx, CAM.cy); v.setIntegrateColor(True)
+    if general:
+        v._cfg.reserved[0] = 1            # debug switch: general depth-first update kernel only
+        v._push()
+    v.reset()
+    return v
+
+
+def test_full_size_stream_properties_2048(tmp_path):
+    # BASELINE.json's full size (640x480 into 2048^3, colour) is too slow for the CPU oracle over a long stream, so the
+    # 40-frame stream is checked through size-independent properties: (1) the fast brick-parallel path and the general
+    # depth-first path (a literal transcription of updateVoxel) agree bit for bit, (2) stored values stay in the
+    # reference's ranges, (3) save -> load -> save is the identity on bytes.
+    fast, slow = _engine_2048(False), _engine_2048(True)
+    upd = 0
+    for f in range(40):
+        pose = synth.orbit_pose(synth.S2, f, 100)
+        cloud = synth.make_frame(synth.S2, pose, CAM, color=True, noise_seed=77, frame=f)
+        fast.integrateCloud(cloud, None, pose)
+        slow.integrateCloud(cloud, None, pose)
+        if f % 13 == 0:
+            assert fast.stats().n_updates == slow.stats().n_updates
+            upd += fast.stats().n_updates
+    assert upd > 1_000_000
+    a, b = fast.download_nodes(), slow.download_nodes()
+    assert len(a["keys"]) > 2_000_000
+    assert_same_nodes(a, b, rgb=True)
+    d, w = a["dw"][:, 0], a["dw"][:, 1]
+    assert w.min() >= 0 and w.max() <= 100.0 and d.min() >= -1.0 and d.max() <= 1.0       # octree.cpp:156-159, hpp:189-198
+    assert ((w == 0) <= (d == -1.0)).all()                                                  # never-observed nodes keep the constructor state
+    lv = a["keys"][:, 0]
+    assert lv.min() == 5 and lv.max() == 11 and not a["split"][lv == 11].any()
+    pa, pb = str(tmp_path / "a.vol"), str(tmp_path / "b.vol")
+    fast.save(pa)
+    again = pkg.TSDFVolumeOctree(device=0, pool_log2=18)
+    again.load(pa); again.save(pb)
+    import hashlib
+    ha = hashlib.sha256(open(pa, "rb").read()).hexdigest(); hb = hashlib.sha256(open(pb, "rb").read()).hexdigest()
+    assert ha == hb
+    # and the render of the reloaded volume is identical
+    pose = synth.orbit_pose(synth.S2, 20, 100)
+    assert np.array_equal(fast.renderView(pose, 4), again.renderView(pose, 4), equal_nan=True)
+
+
+def test_4096_three_tiers_config5_shape():
+    # BASELINE.json configs[4] grid: 4096^3 over 10 m (L=12, C=5, three tiers, coarse cells inside the top bricks)
+    cfg = dict(xres=4096, yres=4096, zres=4096, xsize=10.0, ysize=10.0, zsize=10.0, cx=CAM.cx, cy=CAM.cy)
+    o, e = pair(cfg, 19)
+    assert e.stats().tiers == 3
+    for pose, cloud in frames(synth.S2, 2, stride=3, noise_seed=4):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+        assert e.stats().n_updates == o.stats().n_add_observation
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
