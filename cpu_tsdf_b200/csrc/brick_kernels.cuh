@@ -499,6 +499,8 @@ struct WarpSmem
   int uv[72];
   uint64_t bar;                 // mbarrier of this warp's TMA staging
   uint64_t pad_;
+  signed char rc3[512];         // return codes of the visited finest voxels
+  uint32_t dirty3[16];          // finest voxels whose state changed (bit j3)
 };
 
 __device__ __forceinline__ void path_center (const float* c0, float off, int k, int j, float* c)
@@ -639,36 +641,43 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params
       int2[i2] = __ballot_sync (0xffffffffu, kind2[i2] != KIND_DONE);
       new2[i2] = __ballot_sync (0xffffffffu, kind2[i2] == KIND_NEW);
     }
-    // ---- level 3 (512 finest voxels: j3 = lane + 32 i) ----
-    uint32_t nonneg_mine = 0;                       // lane k (<16) keeps the ballot of iteration k
-#pragma unroll 1
-    for (int i = 0; i < 16; ++i)
+    // ---- level 3: the finest voxels.  Only children of interior level-2 nodes are visited (typically about half
+    //      of the block), so they are COMPACTED across lanes: visited voxel t = lane + 32 r is child (t & 7) of the
+    //      (t >> 3)-th interior level-2 node.  Return codes go to shared memory for the bottom-up sweep. ----
+    if (lane < 16) S.dirty3[lane] = 0;
+    __syncwarp ();
     {
-      const int j3 = lane + 32 * i;
-      const int j2 = j3 >> 3;
-      const bool visited = ((j2 < 32 ? int2[0] : int2[1]) >> (j2 & 31)) & 1;
-      int rc = 0;
-      if (visited)
+      const uint32_t m0 = int2[0], m1 = int2[1];
+      const int n0 = __popc (m0), nvis = 8 * (n0 + __popc (m1));
+#pragma unroll 1
+      for (int base = 0; base < nvis; base += 32)
       {
-        float c[3]; bool u_;
-        path_center (c0, off1, 3, j3, c);
-        visit_node (p, f, S, 72 + j3, false, c, 0.0, false, rc, u_);
-        if (u_) { dirty |= 1u << i; bupd++; }
+        const int t = base + lane;
+        if (t < nvis)
+        {
+          const int rank = t >> 3;
+          const int j2 = rank < n0 ? (int) __fns (m0, 0, rank + 1) : 32 + (int) __fns (m1, 0, rank - n0 + 1);
+          const int j3 = 8 * j2 + (t & 7);
+          float c[3]; bool u_; int rc;
+          path_center (c0, off1, 3, j3, c);
+          visit_node (p, f, S, 72 + j3, false, c, 0.0, false, rc, u_);
+          S.rc3[j3] = (signed char) rc;
+          if (u_) { atomicOr (&S.dirty3[j3 >> 5], 1u << (j3 & 31)); bupd++; }
+        }
       }
-      const uint32_t nn = __ballot_sync (0xffffffffu, visited && rc >= 0);
-      if (lane == i) nonneg_mine = nn;
     }
+    __syncwarp ();
     // ---- bottom-up: level 2 ----
     uint32_t pruned2[2], nonneg2[2];
 #pragma unroll
     for (int i2 = 0; i2 < 2; ++i2)
     {
       const int j2 = lane + 32 * i2;
-      const uint32_t nn = __shfl_sync (0xffffffffu, nonneg_mine, (lane >> 2) + 8 * i2);   // ballot of iteration j2 >> 2
       bool pruned = false;
       if (kind2[i2] != KIND_DONE)
       {
-        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc2[i2] = 1;
+        const uint2 r8 = *reinterpret_cast<const uint2*> (&S.rc3[8 * j2]);               // the eight children's codes (-1 = 0xFF)
+        if (!(r8.x == 0xFFFFFFFFu && r8.y == 0xFFFFFFFFu)) rc2[i2] = 1;
         else
         {
           pruned = true;
@@ -691,10 +700,11 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params
         {
           S.dw[72 + lane + 32 * i] = make_float2 (-1.f, 0.f);
           if (COLOR) S.rgb[72 + lane + 32 * i] = make_uchar4 (0, 0, 0, 0);
-          dirty |= 1u << i;
+          atomicOr (&S.dirty3[i], 1u << lane);
         }
       }
     }
+    __syncwarp ();
     // ---- bottom-up: level 1 ----
     bool pruned1f = false;
     if (lane < 8 && kind1 != KIND_DONE)
@@ -751,7 +761,7 @@ __global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params
     __syncwarp ();
 #pragma unroll 4
     for (int i = 0; i < 16; ++i)
-      if ((dirty >> i) & 1)
+      if ((S.dirty3[i] >> lane) & 1)
       {
         gdw[72 + lane + 32 * i] = S.dw[72 + lane + 32 * i];
         if (COLOR) grgb[72 + lane + 32 * i] = S.rgb[72 + lane + 32 * i];
