@@ -65,7 +65,7 @@ EXPORTS = [
     "b200tsdf_default_config", "b200tsdf_create", "b200tsdf_destroy", "b200tsdf_last_error",
     "b200tsdf_set_config", "b200tsdf_get_config", "b200tsdf_reset", "b200tsdf_integrate",
     "b200tsdf_integrate_device", "b200tsdf_integrate_async", "b200tsdf_sync", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
-    "b200tsdf_free", "b200tsdf_save", "b200tsdf_load", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
+    "b200tsdf_free", "b200tsdf_save", "b200tsdf_load", "b200tsdf_export_shard", "b200tsdf_import_shard", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
     "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_frustum_cull",
     "b200tsdf_profile_begin", "b200tsdf_profile_end",
 ]
@@ -100,6 +100,8 @@ def load_library() -> C.CDLL:
     lib.b200tsdf_mesh.argtypes = [vp, C.c_float, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.b200tsdf_save.argtypes = [vp, C.c_char_p]
     lib.b200tsdf_load.argtypes = [vp, C.c_char_p]
+    lib.b200tsdf_export_shard.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.b200tsdf_import_shard.argtypes = [vp, vp, C.c_size_t]
     lib.b200tsdf_voxel_center.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp]
     lib.b200tsdf_voxel_index.argtypes = [vp, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.b200tsdf_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -317,6 +319,18 @@ class TSDFVolumeOctree:
         """cpp:248-275 — adopts the file's configuration and rebuilds the volume on the device."""
         self._check(self._lib.b200tsdf_load(self._h, filename.encode()))
         self._check(self._lib.b200tsdf_get_config(self._h, C.byref(self._cfg)))
+
+    def export_shard(self) -> np.ndarray:
+        """Everything this (sharded) handle owns, as a byte buffer that any transport can ship."""
+        n = C.c_size_t()
+        self._check(self._lib.b200tsdf_export_shard(self._h, None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._check(self._lib.b200tsdf_export_shard(self._h, _ptr(buf), buf.size, C.byref(n)))
+        return buf
+
+    def import_shard(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._check(self._lib.b200tsdf_import_shard(self._h, _ptr(buf), buf.size))
 
     def getVoxelCenter(self, x, y, z):
         o = np.empty(3, np.float32)

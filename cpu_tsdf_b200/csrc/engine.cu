@@ -253,6 +253,19 @@ __global__ void k_load_bricks (Params p, const uint64_t* __restrict__ keys, int 
   for (int i = threadIdx.x; i < BRICK_SPLIT_WORDS; i += blockDim.x) p.split[s * BRICK_SPLIT_WORDS + i] = split[(size_t) b * BRICK_SPLIT_WORDS + i];
 }
 
+// shard import: scatter coarse-cell (root array) entries
+__global__ void k_import_roots (Params p, int n, const int* __restrict__ idx, const float2* __restrict__ dw, const unsigned char* __restrict__ split,
+                                const uchar4* __restrict__ rgb, const float* __restrict__ M, const int* __restrict__ ns)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = idx[i];
+  p.root_dw[r] = dw[i];
+  if (split[i]) atomicOr (&p.root_split[r >> 5], 1u << (r & 31)); else atomicAnd (&p.root_split[r >> 5], ~(1u << (r & 31)));
+  if (p.root_rgb) p.root_rgb[r] = rgb[i];
+  if (p.root_M) { p.root_M[r] = M[i]; p.root_ns[r] = ns[i]; }
+}
+
 // ---- marching cubes: one warp per allocated brick, warp-scan compaction of the triangle soup ----
 __device__ __forceinline__ bool brick_root_is_split (const Params& p, int t, int bx, int by, int bz)
 {
@@ -1357,6 +1370,125 @@ int b200tsdf_load (b200tsdf_t* h, const char* path)
     cudaFree (dk); cudaFree (dn); cudaFree (ds); cudaFree (dc); cudaFree (dM); cudaFree (dns);
   }
   h->is_empty = is_empty != 0;
+  return check_device_err (h);
+}
+
+
+// ---- shard export / import ------------------------------------------------------------------------------------
+namespace {
+struct ShardHeader { uint32_t magic, version; int32_t L, C, T, Rtop, color, var; uint32_t n_roots, n_bricks; float size; uint32_t pad; };
+constexpr uint32_t SHARD_MAGIC = 0x42325348;   // "B2SH"
+}
+
+int b200tsdf_export_shard (b200tsdf_t* h, void* buf, size_t capacity, size_t* nbytes)
+{
+  if (!h || !nbytes) return B200TSDF_EINVAL;
+  if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "export before reset()");
+  if (h->p.Rtop != h->p.C) return h->fail (B200TSDF_EINVAL, "shard export needs a grid whose coarse cells are the top-tier roots");
+  Snapshot S;
+  int rc = take_snapshot (h, S);
+  if (rc) return rc;
+  const Params& p = S.p;
+  const bool color = p.rgb != nullptr, var = p.M != nullptr;
+  // owned coarse cells and the bricks below them
+  std::vector<int> roots;
+  int n = 1 << p.C;
+  for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z) if (owns_cell (p, x, y, z)) roots.push_back (root_index (p, x, y, z));
+  std::vector<uint32_t> bricks;
+  for (uint32_t s = 0; s <= p.pool_mask; ++s)
+  {
+    uint64_t key = p.keys[s];
+    if (key == KEY_EMPTY) continue;
+    int t = (int) (key >> 60) - 1;
+    int sh = tier_root_level (p, t) - p.C;
+    int bx = (int) ((key >> 40) & 0xFFFFF), by = (int) ((key >> 20) & 0xFFFFF), bz = (int) (key & 0xFFFFF);
+    if (owns_cell (p, bx >> sh, by >> sh, bz >> sh)) bricks.push_back (s);
+  }
+  const size_t root_rec = 4 + 8 + 1 + 4 + 4 + 4, brick_rec = 8 + BRICK_NODES * 8 + BRICK_SPLIT_WORDS * 4 + (color ? BRICK_NODES * 4 : 0) + (var ? BRICK_NODES * 8 : 0);
+  size_t need = sizeof (ShardHeader) + roots.size () * root_rec + bricks.size () * brick_rec;
+  *nbytes = need;
+  if (!buf) return B200TSDF_OK;
+  if (capacity < need) return h->fail (B200TSDF_EINVAL, "export buffer too small");
+  unsigned char* o = (unsigned char*) buf;
+  ShardHeader hd{}; hd.magic = SHARD_MAGIC; hd.version = 1; hd.L = p.L; hd.C = p.C; hd.T = p.T; hd.Rtop = p.Rtop; hd.color = color; hd.var = var;
+  hd.n_roots = (uint32_t) roots.size (); hd.n_bricks = (uint32_t) bricks.size (); hd.size = p.size;
+  std::memcpy (o, &hd, sizeof (hd)); o += sizeof (hd);
+  for (int r : roots)
+  {
+    std::memcpy (o, &r, 4); o += 4;
+    std::memcpy (o, &p.root_dw[r], 8); o += 8;
+    *o++ = (unsigned char) ((p.root_split[r >> 5] >> (r & 31)) & 1);
+    uchar4 c = p.root_rgb ? p.root_rgb[r] : make_uchar4 (0, 0, 0, 0); std::memcpy (o, &c, 4); o += 4;
+    float M = p.root_M ? p.root_M[r] : 0.f; int nsv = p.root_ns ? p.root_ns[r] : 0;
+    std::memcpy (o, &M, 4); o += 4; std::memcpy (o, &nsv, 4); o += 4;
+  }
+  for (uint32_t s : bricks)
+  {
+    std::memcpy (o, &p.keys[s], 8); o += 8;
+    std::memcpy (o, &p.nodes[(size_t) s * BRICK_NODES], BRICK_NODES * 8); o += BRICK_NODES * 8;
+    std::memcpy (o, &p.split[(size_t) s * BRICK_SPLIT_WORDS], BRICK_SPLIT_WORDS * 4); o += BRICK_SPLIT_WORDS * 4;
+    if (color) { std::memcpy (o, &p.rgb[(size_t) s * BRICK_NODES], BRICK_NODES * 4); o += BRICK_NODES * 4; }
+    if (var) { std::memcpy (o, &p.M[(size_t) s * BRICK_NODES], BRICK_NODES * 4); o += BRICK_NODES * 4; std::memcpy (o, &p.ns[(size_t) s * BRICK_NODES], BRICK_NODES * 4); o += BRICK_NODES * 4; }
+  }
+  return B200TSDF_OK;
+}
+
+int b200tsdf_import_shard (b200tsdf_t* h, const void* buf, size_t nbytes)
+{
+  if (!h || !buf || nbytes < sizeof (ShardHeader)) return B200TSDF_EINVAL;
+  if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "import before reset()");
+  const Params& p = h->p;
+  ShardHeader hd; std::memcpy (&hd, buf, sizeof (hd));
+  const bool color = p.rgb != nullptr, var = p.M != nullptr;
+  if (hd.magic != SHARD_MAGIC || hd.version != 1) return h->fail (B200TSDF_EINVAL, "not a shard buffer");
+  if (hd.L != p.L || hd.C != p.C || hd.T != p.T || hd.Rtop != p.Rtop || hd.size != p.size || (hd.color != 0) != color || (hd.var != 0) != var)
+    return h->fail (B200TSDF_EINVAL, "shard was exported from a different grid configuration");
+  const size_t root_rec = 4 + 8 + 1 + 4 + 4 + 4, brick_rec = 8 + BRICK_NODES * 8 + BRICK_SPLIT_WORDS * 4 + (color ? BRICK_NODES * 4 : 0) + (var ? BRICK_NODES * 8 : 0);
+  if (nbytes != sizeof (ShardHeader) + (size_t) hd.n_roots * root_rec + (size_t) hd.n_bricks * brick_rec) return h->fail (B200TSDF_EINVAL, "truncated shard buffer");
+  cudaSetDevice (h->device);
+  int rc = b200tsdf_sync (h);
+  if (rc) return rc;
+  const unsigned char* o = (const unsigned char*) buf + sizeof (ShardHeader);
+  size_t nr = hd.n_roots, nb = hd.n_bricks;
+  std::vector<int> ridx (nr); std::vector<float2> rdw (nr); std::vector<unsigned char> rsp (nr); std::vector<uchar4> rrgb (nr); std::vector<float> rM (nr); std::vector<int> rns (nr);
+  for (size_t i = 0; i < nr; ++i)
+  {
+    std::memcpy (&ridx[i], o, 4); o += 4; std::memcpy (&rdw[i], o, 8); o += 8; rsp[i] = *o++;
+    std::memcpy (&rrgb[i], o, 4); o += 4; std::memcpy (&rM[i], o, 4); o += 4; std::memcpy (&rns[i], o, 4); o += 4;
+    if (ridx[i] < 0 || (size_t) ridx[i] >= h->root_n) return h->fail (B200TSDF_EINVAL, "corrupt shard buffer");
+  }
+  std::vector<uint64_t> keys (nb); std::vector<float2> nodes (nb * BRICK_NODES); std::vector<uint32_t> split (nb * BRICK_SPLIT_WORDS);
+  std::vector<uchar4> rgb (color ? nb * BRICK_NODES : 0); std::vector<float> Mv (var ? nb * BRICK_NODES : 0); std::vector<int> nsv (var ? nb * BRICK_NODES : 0);
+  for (size_t i = 0; i < nb; ++i)
+  {
+    std::memcpy (&keys[i], o, 8); o += 8;
+    std::memcpy (&nodes[i * BRICK_NODES], o, BRICK_NODES * 8); o += BRICK_NODES * 8;
+    std::memcpy (&split[i * BRICK_SPLIT_WORDS], o, BRICK_SPLIT_WORDS * 4); o += BRICK_SPLIT_WORDS * 4;
+    if (color) { std::memcpy (&rgb[i * BRICK_NODES], o, BRICK_NODES * 4); o += BRICK_NODES * 4; }
+    if (var) { std::memcpy (&Mv[i * BRICK_NODES], o, BRICK_NODES * 4); o += BRICK_NODES * 4; std::memcpy (&nsv[i * BRICK_NODES], o, BRICK_NODES * 4); o += BRICK_NODES * 4; }
+  }
+  cudaStream_t s = h->stream;
+  auto up = [&] (const void* src, size_t bytes, void** dst) -> cudaError_t { if (!bytes) { *dst = nullptr; return cudaSuccess; } cudaError_t e = cudaMalloc (dst, bytes); if (e != cudaSuccess) return e; return cudaMemcpy (*dst, src, bytes, cudaMemcpyHostToDevice); };
+  void *d_idx = nullptr, *d_dw = nullptr, *d_sp = nullptr, *d_rgb = nullptr, *d_M = nullptr, *d_ns = nullptr;
+  if (nr)
+  {
+    CK (up (ridx.data (), nr * 4, &d_idx)); CK (up (rdw.data (), nr * 8, &d_dw)); CK (up (rsp.data (), nr, &d_sp));
+    CK (up (rrgb.data (), nr * 4, &d_rgb)); CK (up (rM.data (), nr * 4, &d_M)); CK (up (rns.data (), nr * 4, &d_ns));
+    k_import_roots<<<(unsigned) ((nr + 127) / 128), 128, 0, s>>> (p, (int) nr, (const int*) d_idx, (const float2*) d_dw, (const unsigned char*) d_sp, (const uchar4*) d_rgb, (const float*) d_M, (const int*) d_ns);
+    CK (cudaStreamSynchronize (s));
+    cudaFree (d_idx); cudaFree (d_dw); cudaFree (d_sp); cudaFree (d_rgb); cudaFree (d_M); cudaFree (d_ns);
+  }
+  if (nb)
+  {
+    void *dk = nullptr, *dn = nullptr, *ds = nullptr, *dc = nullptr, *dM = nullptr, *dns = nullptr;
+    CK (up (keys.data (), nb * 8, &dk)); CK (up (nodes.data (), nb * BRICK_NODES * 8, &dn)); CK (up (split.data (), nb * BRICK_SPLIT_WORDS * 4, &ds));
+    if (color) CK (up (rgb.data (), nb * BRICK_NODES * 4, &dc));
+    if (var) { CK (up (Mv.data (), nb * BRICK_NODES * 4, &dM)); CK (up (nsv.data (), nb * BRICK_NODES * 4, &dns)); }
+    k_load_bricks<<<(unsigned) nb, 128, 0, s>>> (p, (const uint64_t*) dk, (int) nb, (const float2*) dn, (const uint32_t*) ds, (const uchar4*) dc, (const float*) dM, (const int*) dns);
+    CK (cudaStreamSynchronize (s));
+    cudaFree (dk); cudaFree (dn); cudaFree (ds); cudaFree (dc); cudaFree (dM); cudaFree (dns);
+  }
+  h->is_empty = false;
   return check_device_err (h);
 }
 

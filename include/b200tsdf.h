@@ -117,6 +117,15 @@ int  b200tsdf_save (b200tsdf_t* h, const char* path);
  * OctreeNode::M_/nsample_ are kept only if track_variance was set on the handle. */
 int  b200tsdf_load (b200tsdf_t* h, const char* path);
 
+/* Shard gather (multi-GPU): a handle created with shard_count > 1 owns the coarse cells with
+ * hash(cell) % shard_count == shard_rank.  b200tsdf_export_shard serialises everything this handle owns (the
+ * coarse-cell entries and every brick below them) into a host buffer (*nbytes needed; pass buf == NULL to query);
+ * b200tsdf_import_shard merges such a buffer into a handle with the same grid configuration.  Importing all
+ * shards into one volume reproduces the unsharded volume bit for bit; rendering, queries and meshing then run on
+ * that volume.  Only grids whose coarse cells are the top-tier roots are supported (e.g. 2048^3/10 m, 512^3/3 m). */
+int  b200tsdf_export_shard (b200tsdf_t* h, void* buf, size_t capacity, size_t* nbytes);
+int  b200tsdf_import_shard (b200tsdf_t* h, const void* buf, size_t nbytes);
+
 /* getVoxelCenter / getVoxelIndex (cpp:553-574) */
 int  b200tsdf_voxel_center (const b200tsdf_t* h, int64_t x, int64_t y, int64_t z, float* out3);
 int  b200tsdf_voxel_index (const b200tsdf_t* h, float x, float y, float z, int32_t* out3, int32_t* inside);

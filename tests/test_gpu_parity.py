@@ -303,7 +303,7 @@ def test_full_size_stream_properties_2048(tmp_path):
     assert ha == hb
     # and the render of the reloaded volume is identical
     pose = synth.orbit_pose(synth.S2, 20, 100)
-    assert np.array_equal(fast.renderView(pose, 4), again.renderView(pose, 4), equal_nan=True)
+    assert np.array_equal(fast.renderView(pose, 4), again.renderView(pose, 4), equal_nan=True)   # (same wrapper on both sides)
 
 
 def test_4096_three_tiers_config5_shape():
@@ -315,3 +315,30 @@ def test_4096_three_tiers_config5_shape():
         o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
         assert e.stats().n_updates == o.stats().n_add_observation
     assert_same_nodes(o.dump_nodes(), e.download_nodes())
+
+
+def test_shards_gathered_into_one_volume_render_like_the_whole():
+    # multi-GPU read side: integrate in shards, gather the shards into one volume, render / mesh there
+    o = OracleVolume(**CFG_512); o.reset()
+    shards = []
+    for r in range(3):
+        v = pkg.TSDFVolumeOctree(device=0, pool_log2=17, shard_rank=r, shard_count=3)
+        v.setResolution(512, 512, 512); v.setCameraIntrinsics(525.0, 525.0, CAM.cx, CAM.cy); v.reset()
+        shards.append(v)
+    for pose, cloud in frames(synth.S1, 4, stride=11, noise_seed=21):
+        o.integrate(cloud, pose)
+        for v in shards:
+            v.integrateCloud(cloud, None, pose)
+    whole = pkg.TSDFVolumeOctree(device=0, pool_log2=18)
+    whole.setResolution(512, 512, 512); whole.setCameraIntrinsics(525.0, 525.0, CAM.cx, CAM.cy); whole.reset()
+    for v in shards:
+        whole.import_shard(v.export_shard())
+    assert_same_nodes(o.dump_nodes(), whole.download_nodes())
+    pose = synth.orbit_pose(synth.S1, 17, 100)
+    ra, rb = o.render(pose, 2), whole.renderView(pose, 2)
+    assert np.isfinite(ra[..., 2]).sum() > 20000
+    assert np.array_equal(ra[..., :3], rb[..., :3], equal_nan=True) and np.array_equal(ra[..., 4:7], rb[..., 4:7], equal_nan=True)
+    with pytest.raises(pkg.B200Error):
+        other = pkg.TSDFVolumeOctree(device=0, pool_log2=12)
+        other.setResolution(256, 256, 256); other.reset()
+        other.import_shard(shards[0].export_shard())          # different grid
