@@ -1073,6 +1073,21 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
       for (int i = 0; i < 16; ++i) { k3[i] = top->kind[73 + lane + 32 * i]; r3[i] = top->rc[73 + lane + 32 * i]; }
 #pragma unroll
       for (int i = 0; i < 16; ++i) if (k3[i] != KIND_DONE) r3[i] = gq[(size_t) ci * STRIDE + 73 + lane + 32 * i].rc;
+      // block roots that k_blocks handed back untouched (prune-then-resplit inside the block): general path, rare
+#pragma unroll 1
+      for (int i = 0; i < 16; ++i)
+        if (k3[i] != KIND_DONE && r3[i] == RC_DEFERRED)
+        {
+          const int j3 = lane + 32 * i;
+          NodePos n; float c[3];
+          path_center (c0, off1, 3, j3, c);
+          int lx = 0, ly = 0, lz = 0;
+          for (int q = 2; q >= 0; --q) { int cc = (j3 >> (3 * q)) & 7; lx = (lx << 1) | (cc >> 2); ly = (ly << 1) | ((cc >> 1) & 1); lz = (lz << 1) | (cc & 1); }
+          n.level = p.C + 3; n.x = (cell.x << 3) | lx; n.y = (cell.y << 3) | ly; n.z = (cell.z << 3) | lz;
+          n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.125f; n.slot = t1; n.idx = 72 + j3;
+          if (k3[i] == KIND_NEW) atomicAnd (&gsw[4 + (j3 >> 5)], ~(1u << (j3 & 31)));      // undo the speculative split
+          r3[i] = upper_fold_slow (p, f, n, upd, vis);
+        }
 #pragma unroll
       for (int i = 0; i < 16; ++i)
       {

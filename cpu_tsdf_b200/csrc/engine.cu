@@ -111,8 +111,16 @@ __global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restr
 // frame front end in ONE launch: blocks [0, cull_blocks) run the frustum cull of the coarse cells, the
 // rest the per-pixel pre-split.  The two are independent (the cull reads only geometry).  The work-list
 // counters and the statistics snapshot are reset by k_frame_begin on the previous launch boundary.
-__global__ void k_front (Params p, Frame f, Planes P, int cull_blocks, int* __restrict__ list, int* __restrict__ count, QNode* __restrict__ q0)
+__global__ void k_front (Params p, Frame f, Planes P, int cull_blocks, int* __restrict__ list, int* __restrict__ count, QNode* __restrict__ q0,
+                         unsigned long long* __restrict__ stats, int* __restrict__ next_counts)
 {
+  // frame-begin bookkeeping (was a launch of its own): snapshot the cumulative counters, and clear the counter
+  // set the NEXT frame will use (the sets alternate, so nothing in this frame touches it)
+  if (blockIdx.x == 0 && threadIdx.x < 16)
+  {
+    if (threadIdx.x < ST_N) stats[ST_N + threadIdx.x] = stats[threadIdx.x];
+    next_counts[threadIdx.x] = 0;
+  }
   if ((int) blockIdx.x < cull_blocks)
   {
     int n = 1 << p.C;
@@ -373,6 +381,7 @@ struct b200tsdf
   cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   uint64_t frame_no = 0;
+  int count_set = 0;             // which of the two per-frame counter sets the last frame used
   int* d_culled = nullptr; int* d_count = nullptr; unsigned long long* d_stats = nullptr;
   size_t culled_cap = 0;
   bool timed = false;
@@ -458,7 +467,7 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
          && cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking) == cudaSuccess
          && cudaStreamCreateWithFlags (&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess
          && cudaMalloc (&h->d_err, sizeof (int)) == cudaSuccess
-         && cudaMalloc (&h->d_count, 16 * sizeof (int)) == cudaSuccess
+         && cudaMalloc (&h->d_count, 64 * sizeof (int)) == cudaSuccess
          && cudaMalloc (&h->d_stats, ST_TOTAL * sizeof (unsigned long long)) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i)
     ok = cudaEventCreateWithFlags (&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess
@@ -624,6 +633,8 @@ int b200tsdf_reset (b200tsdf_t* h)
   if (color) CK (cudaMemsetAsync (p.root_rgb, 0, root_n * sizeof (uchar4), s));
   if (var) { CK (cudaMemsetAsync (p.root_M, 0, root_n * sizeof (float), s)); CK (cudaMemsetAsync (p.root_ns, 0, root_n * sizeof (int), s)); }
   CK (cudaMemsetAsync (h->d_err, 0, sizeof (int), s));
+  CK (cudaMemsetAsync (h->d_count, 0, 64 * sizeof (int), s));
+  h->count_set = 0;
   CK (cudaMemsetAsync (h->d_stats, 0, ST_TOTAL * sizeof (unsigned long long), s));
   h->kring_pending = 0; h->kring_head = 0;
   if (Rtop < C) k_insert_top_bricks<<<(unsigned) ((root_n + 127) / 128), 128, 0, s>>> (p);
@@ -646,21 +657,25 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   b2host::frustum_planes (pose, p.width, p.height, p.fx, p.fy, p.min_sensor, p.max_sensor, P.pl);
   cudaStream_t s = h->stream;
   CK (cudaEventRecord (h->ev_t0, s));
-  k_frame_begin<<<1, 32, 0, s>>> (h->d_stats, h->d_count);
+  // counter sets alternate between frames: this frame uses `cnt`, k_front clears the other one for the next frame
+  h->count_set ^= 1;
+  int* cnt = h->d_count + 16 * h->count_set;
+  int* cnt_next = h->d_count + 16 * (h->count_set ^ 1);
+  h->Q.n = cnt;
   int npix = W * H;
   int ncells = 1 << (3 * p.C);
   {
     const int cull_blocks = (ncells + 255) / 256;
-    k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, f, P, cull_blocks, h->d_culled, h->d_count, h->fast_path ? h->Q.q[0] : nullptr);
+    k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, f, P, cull_blocks, h->d_culled, cnt, h->fast_path ? h->Q.q[0] : nullptr, h->d_stats, cnt_next);
   }
-  h->launches += 2;
+  h->launches += 1;
   // dominant kernel, bracketed by a ring of event pairs so bench.py can average its launch duration
   if (h->kring_pending >= KRING) h->drain_kring (KRING / 2);
   int kr = h->kring_head;
   if (h->fast_path)
   {
     const int nl = h->q_levels;
-    int* d_bcount = h->d_count + 9; int* d_bailcount = h->d_count + 10;
+    int* d_bcount = cnt + 9; int* d_bailcount = cnt + 10;
     Queues Qb = h->Q;
     int bli = nl - 1;
     if (h->cell_path)
@@ -670,34 +685,34 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
       bli = NL;
       if (h->top_path)
       {
-        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
-        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       }
-      else if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
-      else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
-      else k_cell_down<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      else if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      else k_cell_down<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       h->launches++;
     }
     else
       for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
     CK (cudaEventRecord (h->kring[kr][0], s));
-    int* bail_list = (h->cell_path && !h->top_path) ? nullptr : h->d_bail;   // the generic per-cell bottom-up sweep redoes deferred block roots itself
-    if (p.color) k_blocks<true><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, h->d_count + 11, h->d_stats);
-    else k_blocks<false><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, h->d_count + 11, h->d_stats);
+    int* bail_list = h->cell_path ? nullptr : h->d_bail;       // the per-cell bottom-up sweeps redo deferred block roots themselves
+    if (p.color) k_blocks<true><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, cnt + 11, h->d_stats);
+    else k_blocks<false><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, cnt + 11, h->d_stats);
     CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
-    if (!h->cell_path || h->top_path) { k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats); h->launches++; }
+    if (!h->cell_path) { k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats); h->launches++; }
     if (h->cell_path)
     {
       const int NL = h->cell_nl;
       if (h->top_path)
       {
-        if (p.color) k_celltop_up<true><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
-        else k_celltop_up<false><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        if (p.color) k_celltop_up<true><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        else k_celltop_up<false><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
       }
-      else if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
-      else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
-      else k_cell_up<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->d_count, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      else if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      else k_cell_up<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
       h->launches++;
     }
     else
@@ -707,7 +722,7 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   {
     CK (cudaEventRecord (h->kring[kr][0], s));
     // general path: every culled cell depth-first (grid covers the worst case; threads past *count exit)
-    k_update_dfs<<<(ncells + 31) / 32, 32, 0, s>>> (p, f, h->d_culled, h->d_count, h->d_stats);
+    k_update_dfs<<<(ncells + 31) / 32, 32, 0, s>>> (p, f, h->d_culled, cnt, h->d_stats);
     CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
   }
@@ -786,7 +801,7 @@ int b200tsdf_get_stats (b200tsdf_t* h, b200tsdf_stats* s)
   if (rc) return rc;
   unsigned long long st[2 * ST_N]; int cnt[16];
   CK (cudaMemcpy (st, h->d_stats, sizeof (st), cudaMemcpyDeviceToHost));
-  CK (cudaMemcpy (cnt, h->d_count, sizeof (cnt), cudaMemcpyDeviceToHost));
+  CK (cudaMemcpy (cnt, h->d_count + 16 * h->count_set, sizeof (cnt), cudaMemcpyDeviceToHost));
   h->d2h_bytes += (long long) (sizeof (st) + sizeof (cnt));
   s->n_updates = (int64_t) (st[ST_UPDATES] - st[ST_N + ST_UPDATES]);
   s->n_node_visits = (int64_t) (st[ST_VISITS] - st[ST_N + ST_VISITS]);
@@ -797,7 +812,7 @@ int b200tsdf_get_stats (b200tsdf_t* h, b200tsdf_stats* s)
   s->pool_capacity = (int64_t) h->pool;
   s->coarse_level = h->p.C; s->finest_level = h->p.L; s->tiers = h->p.T;
   // allocated bricks
-  int* d_n = h->d_count + 8;
+  int* d_n = h->d_count + 40;
   CK (cudaMemset (d_n, 0, sizeof (int)));
   int* d_list = nullptr;
   CK (cudaMalloc (&d_list, h->pool * sizeof (int)));
@@ -883,7 +898,7 @@ int b200tsdf_mesh (b200tsdf_t* h, float w_min, int color_mode, float** verts, ui
   McParams mc;
   make_mc_params (h->cfg, p, w_min, color_mode, mc);
   cudaStream_t s = h->stream;
-  int* d_list = nullptr; int* d_n = h->d_count + 8;
+  int* d_list = nullptr; int* d_n = h->d_count + 40;
   unsigned long long* d_total = h->d_stats + ST_SCRATCH;
   CK (cudaMalloc (&d_list, h->pool * sizeof (int)));
   CK (cudaMemsetAsync (d_n, 0, sizeof (int), s));
@@ -1025,7 +1040,7 @@ int take_snapshot (b200tsdf* h, Snapshot& S)
   if (rc) return rc;
   const Params& dp = h->p;
   cudaStream_t s = h->stream;
-  int* d_list = nullptr; int* d_n = h->d_count + 8;
+  int* d_list = nullptr; int* d_n = h->d_count + 40;
   CK (cudaMalloc (&d_list, h->pool * sizeof (int)));
   CK (cudaMemsetAsync (d_n, 0, sizeof (int), s));
   k_list_bricks<<<(unsigned) ((h->pool + 255) / 256), 256, 0, s>>> (dp, d_list, d_n);
