@@ -412,6 +412,17 @@ struct b200tsdf
   }
   std::string err;
   float* mesh_v = nullptr; unsigned char* mesh_c = nullptr;
+  // grow-only device scratch for the read-side calls (queries, render): no allocation per call
+  unsigned char* d_scratch = nullptr; size_t scratch_cap = 0;
+  int scratch (size_t bytes)
+  {
+    if (bytes <= scratch_cap) return 0;
+    cudaFree (d_scratch); d_scratch = nullptr; scratch_cap = 0;
+    size_t want = bytes + bytes / 2 + 4096;
+    if (cudaMalloc (&d_scratch, want) != cudaSuccess) return fail (B200TSDF_ENOMEM, "device scratch allocation failed");
+    scratch_cap = want;
+    return 0;
+  }
 
   int fail (int code, const std::string& m) { err = m; return code; }
 };
@@ -493,7 +504,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   if (h->stream) cudaStreamSynchronize (h->stream);
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
   free_volume (h);
-  cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled);
+  cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled); cudaFree (h->d_scratch);
   cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
@@ -741,6 +752,8 @@ int b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t strid
   if (!h || !d_points || !pose) return B200TSDF_EINVAL;
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
   if (width <= 0 || height <= 0 || stride < 12) return h->fail (B200TSDF_EINVAL, "bad cloud shape");
+  if (width != h->cfg.image_width || height != h->cfg.image_height)
+    return h->fail (B200TSDF_EINVAL, "organized cloud size differs from setImageSize()");
   cudaSetDevice (h->device);
   return integrate_on_device (h, (const unsigned char*) d_points, stride, xyz_off, rgba_off, width, height, pose);
 }
@@ -751,6 +764,8 @@ static int integrate_host (b200tsdf* h, const void* points, size_t stride, int x
   if (!h || !points || !pose) return B200TSDF_EINVAL;
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
   if (width <= 0 || height <= 0 || stride < 12) return h->fail (B200TSDF_EINVAL, "bad cloud shape");
+  if (width != h->cfg.image_width || height != h->cfg.image_height)
+    return h->fail (B200TSDF_EINVAL, "organized cloud size differs from setImageSize() (the reference indexes cloud(u,v) with the image size, cpp:611-617)");
   cudaSetDevice (h->device);
   size_t bytes = (size_t) width * height * stride;
   if (bytes > h->frame_cap)
@@ -841,9 +856,13 @@ int b200tsdf_query (b200tsdf_t* h, const float* xyz, int n, int what, int mode,
   if (((what & 1) && !val) || ((what & 2) && !grad) || ((what & 4) && !hess)) return h->fail (B200TSDF_EINVAL, "missing output buffer");
   if (n == 0) return B200TSDF_OK;
   cudaSetDevice (h->device);
-  float *d_xyz = nullptr, *d_val = nullptr, *d_grad = nullptr, *d_hess = nullptr; unsigned char* d_ok = nullptr;
-  CK (cudaMalloc (&d_xyz, (size_t) n * 12)); CK (cudaMalloc (&d_val, (size_t) n * 4));
-  CK (cudaMalloc (&d_grad, (size_t) n * 12)); CK (cudaMalloc (&d_hess, (size_t) n * 36)); CK (cudaMalloc (&d_ok, (size_t) n));
+  // one scratch block: xyz (12n) | val (4n) | grad (12n) | hess (36n) | ok (n)
+  { int rc = h->scratch ((size_t) n * 65 + 64); if (rc) return rc; }
+  float* d_xyz = (float*) h->d_scratch;
+  float* d_val = d_xyz + (size_t) 3 * n;
+  float* d_grad = d_val + n;
+  float* d_hess = d_grad + (size_t) 3 * n;
+  unsigned char* d_ok = (unsigned char*) (d_hess + (size_t) 9 * n);
   cudaStream_t s = h->stream;
   CK (cudaMemcpyAsync (d_xyz, xyz, (size_t) n * 12, cudaMemcpyHostToDevice, s));
   k_query<<<(n + 127) / 128, 128, 0, s>>> (h->p, d_xyz, n, what, mode, d_val, d_grad, d_hess, d_ok);
@@ -852,7 +871,6 @@ int b200tsdf_query (b200tsdf_t* h, const float* xyz, int n, int what, int mode,
   if (what & 2) CK (cudaMemcpyAsync (grad, d_grad, (size_t) n * 12, cudaMemcpyDeviceToHost, s));
   if (what & 4) CK (cudaMemcpyAsync (hess, d_hess, (size_t) n * 36, cudaMemcpyDeviceToHost, s));
   CK (cudaStreamSynchronize (s));
-  cudaFree (d_xyz); cudaFree (d_val); cudaFree (d_grad); cudaFree (d_hess); cudaFree (d_ok);
   return B200TSDF_OK;
 }
 
@@ -868,9 +886,9 @@ int b200tsdf_render (b200tsdf_t* h, const double* pose, int downsample, void* ou
   if (p.width / downsample <= 0 || p.height / downsample <= 0) return h->fail (B200TSDF_EINVAL, "downsample too large");
   make_render_params (h->cfg, p, pose, downsample, r);
   size_t npix = (size_t) r.width * r.height;
-  float* d_out = nullptr; unsigned char* d_rgb = nullptr;
-  CK (cudaMalloc (&d_out, npix * 6 * sizeof (float)));
-  if (rgb_out) CK (cudaMalloc (&d_rgb, npix * 3));
+  { int rc = h->scratch (npix * 6 * sizeof (float) + npix * 3 + 64); if (rc) return rc; }
+  float* d_out = (float*) h->d_scratch;
+  unsigned char* d_rgb = rgb_out ? h->d_scratch + npix * 6 * sizeof (float) : nullptr;
   cudaStream_t s = h->stream;
   dim3 grid ((r.width + 7) / 8, (r.height + 7) / 8);
   k_render<<<grid, 64, 0, s>>> (p, r, d_out, d_rgb);
@@ -878,7 +896,6 @@ int b200tsdf_render (b200tsdf_t* h, const double* pose, int downsample, void* ou
   CK (cudaMemcpyAsync (tmp.data (), d_out, npix * 6 * sizeof (float), cudaMemcpyDeviceToHost, s));
   if (rgb_out) CK (cudaMemcpyAsync (rgb_out, d_rgb, npix * 3, cudaMemcpyDeviceToHost, s));
   CK (cudaStreamSynchronize (s));
-  cudaFree (d_out); cudaFree (d_rgb);
   unsigned char* base = (unsigned char*) out;
   for (size_t i = 0; i < npix; ++i)
   {

@@ -200,6 +200,17 @@ def test_errors_are_reported_not_thrown():
     with pytest.raises(pkg.B200Error):
         v.reset()                                                              # not a power of two
     v.setResolution(256, 256, 256); v.reset()
+    with pytest.raises(pkg.B200Error):
+        v.integrateCloud(np.zeros((4, 4, 4), np.float32), None, np.eye(4))     # cloud is not image-sized
+    # repeated single-point queries reuse the handle's scratch (no allocation per call) and stay consistent
+    pose0 = synth.orbit_pose(synth.S1, 0, 1)
+    v.setCameraIntrinsics(525, 525, CAM.cx, CAM.cy)
+    v.integrateCloud(synth.make_frame(synth.S1, pose0, CAM), None, pose0)
+    pts = query_points(seed=5, n=64)
+    bval, _, _, bok = v._query(pts, 7, 1)
+    for i in range(0, 64, 7):
+        val, _, _, ok = v._query(pts[i:i + 1], 7, 1)
+        assert ok[0] == bok[i] and np.array_equal(val.view(np.uint32), bval[i:i + 1].view(np.uint32))
     # a pool that is too small must surface as ENOMEM, not corrupt memory
     small = pkg.TSDFVolumeOctree(device=0, pool_log2=8)
     small.setResolution(512, 512, 512); small.setCameraIntrinsics(525, 525, CAM.cx, CAM.cy); small.reset()
