@@ -61,10 +61,15 @@ class Profile(C.Structure):
     ]
 
 
+class OrganizeOpts(C.Structure):
+    """b200tsdf_organize_opts"""
+    _fields_ = [("cloud_units", C.c_float), ("zero_nans", C.c_int32), ("world_to_camera", C.c_void_p)]
+
+
 EXPORTS = [
     "b200tsdf_default_config", "b200tsdf_create", "b200tsdf_destroy", "b200tsdf_last_error",
     "b200tsdf_set_config", "b200tsdf_get_config", "b200tsdf_reset", "b200tsdf_integrate",
-    "b200tsdf_integrate_device", "b200tsdf_integrate_async", "b200tsdf_sync", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
+    "b200tsdf_integrate_device", "b200tsdf_integrate_async", "b200tsdf_sync", "b200tsdf_organize", "b200tsdf_integrate_unorganized", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
     "b200tsdf_free", "b200tsdf_save", "b200tsdf_load", "b200tsdf_export_shard", "b200tsdf_import_shard", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
     "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_frustum_cull",
     "b200tsdf_profile_begin", "b200tsdf_profile_end",
@@ -95,6 +100,8 @@ def load_library() -> C.CDLL:
     lib.b200tsdf_integrate_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_integrate_async.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_sync.argtypes = [vp]
+    lib.b200tsdf_organize.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(OrganizeOpts), vp, C.c_size_t, C.c_int, C.POINTER(C.c_int64)]
+    lib.b200tsdf_integrate_unorganized.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(OrganizeOpts), vp]
     lib.b200tsdf_query.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.b200tsdf_render.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, vp]
     lib.b200tsdf_mesh.argtypes = [vp, C.c_float, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -258,6 +265,40 @@ class TSDFVolumeOctree:
 
     def sync(self):
         self._check(self._lib.b200tsdf_sync(self._h))
+
+    @staticmethod
+    def _org_opts(cloud_units, zero_nans, world_to_camera):
+        tf = None if world_to_camera is None else np.ascontiguousarray(world_to_camera, dtype=np.float64).reshape(4, 4)
+        opts = OrganizeOpts(float(cloud_units), int(bool(zero_nans)), None if tf is None else tf.ctypes.data)
+        return opts, tf                                    # tf is returned to keep it alive across the call
+
+    def organizeCloud(self, points: np.ndarray, *, cloud_units=1.0, zero_nans=False, world_to_camera=None):
+        """The z-buffer re-organisation of the reference's `integrate` program (integrate.cpp:548-607) for an
+        unorganised cloud [n, 3] (or [n, 8] rows in pcl::PointXYZRGBA layout).  Returns ([H, W, 8] float32 rows in
+        PointXYZRGBA layout, number of filled pixels)."""
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        if pts.ndim != 2 or pts.shape[1] < 3:
+            raise ValueError("points must be [n, >=3] float32")
+        W, H = self._cfg.image_width, self._cfg.image_height
+        out = np.empty((H, W, 8), np.float32)
+        opts, _keep = self._org_opts(cloud_units, zero_nans, world_to_camera)
+        filled = C.c_int64(0)
+        self._check(self._lib.b200tsdf_organize(self._h, _ptr(pts), pts.shape[0], pts.strides[0], 0, 16 if pts.shape[1] >= 5 else -1,
+                                                C.byref(opts), _ptr(out), 32, 16, C.byref(filled)))
+        return out, int(filled.value)
+
+    def integrateUnorganizedCloud(self, points: np.ndarray, trans=np.eye(4), *, cloud_units=1.0, zero_nans=False,
+                                  world_to_camera=None) -> bool:
+        """integrate.cpp:582-635 + :673 in one call: z-buffer on the GPU, then integrateCloud, without the organized
+        cloud leaving device memory."""
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        if pts.ndim != 2 or pts.shape[1] < 3:
+            raise ValueError("points must be [n, >=3] float32")
+        opts, _keep = self._org_opts(cloud_units, zero_nans, world_to_camera)
+        pose = _pose(trans)
+        self._check(self._lib.b200tsdf_integrate_unorganized(self._h, _ptr(pts), pts.shape[0], pts.strides[0], 0,
+                                                             16 if pts.shape[1] >= 5 else -1, C.byref(opts), _ptr(pose)))
+        return True
 
     def _query(self, pts, what, mode):
         xyz = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)

@@ -8,6 +8,7 @@
 #include "host_math.h"
 #include "params_setup.h"
 #include "brick_kernels.cuh"
+#include "organize.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -797,6 +798,81 @@ int b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int xy
 int b200tsdf_integrate_async (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
                               int width, int height, const double* pose)
 { return integrate_host (h, points, stride, xyz_off, rgba_off, width, height, pose, false); }
+
+// ---- unorganised clouds (integrate.cpp:548-635) ------------------------------------------------
+namespace {
+
+// uploads the points, z-buffers them and writes the organized cloud to d_out (device).  Scratch layout:
+// [points n*stride | zkey npix*8 | filled counter 8 | organized npix*out_stride (when d_out == nullptr)]
+int organize_on_device (b200tsdf* h, const void* points, size_t n, size_t stride, int xyz_off, int rgba_off,
+                        const b200tsdf_organize_opts* opts, size_t out_stride, int out_rgba_off,
+                        unsigned char** d_out, unsigned long long** d_filled)
+{
+  if (!h || (!points && n) || !opts) return B200TSDF_EINVAL;
+  if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "organize before reset() (the image size and intrinsics are read at reset)");
+  if (stride < 12 || xyz_off < 0 || (size_t) xyz_off + 12 > stride || (rgba_off >= 0 && (size_t) rgba_off + 4 > stride))
+    return h->fail (B200TSDF_EINVAL, "bad point layout");
+  if (out_stride < 16 || (out_stride & 3) || (out_rgba_off >= 0 && ((size_t) out_rgba_off + 4 > out_stride || out_rgba_off < 12)))
+    return h->fail (B200TSDF_EINVAL, "bad organized layout");
+  if (n >= (1ull << 32)) return h->fail (B200TSDF_EINVAL, "more than 2^32-1 points in one cloud");
+  cudaSetDevice (h->device);
+  OrgParams o{};
+  // the program keeps its intrinsics as float globals (integrate.cpp:63-68, 349-361)
+  o.fx = (float) h->cfg.fx; o.fy = (float) h->cfg.fy; o.cx = (float) h->cfg.cx; o.cy = (float) h->cfg.cy;
+  o.width = h->cfg.image_width; o.height = h->cfg.image_height;
+  o.cloud_units = opts->cloud_units; o.zero_nans = opts->zero_nans; o.has_tf = opts->world_to_camera != nullptr;
+  if (o.has_tf) for (int i = 0; i < 12; ++i) o.tf[i] = opts->world_to_camera[i];
+  size_t npix = (size_t) o.width * o.height;
+  size_t off_key = (n * stride + 255) & ~(size_t) 255, off_cnt = off_key + npix * 8, off_out = off_cnt + 256;
+  { int rc = h->scratch (off_out + npix * out_stride + 64); if (rc) return rc; }
+  unsigned char* d_pts = h->d_scratch;
+  unsigned long long* zkey = (unsigned long long*) (h->d_scratch + off_key);
+  *d_filled = (unsigned long long*) (h->d_scratch + off_cnt);
+  *d_out = h->d_scratch + off_out;
+  cudaStream_t s = h->stream;
+  if (n) { CK (cudaMemcpyAsync (d_pts, points, n * stride, cudaMemcpyHostToDevice, s)); h->h2d_bytes += (long long) (n * stride); }
+  k_org_clear<<<(unsigned) ((npix + 255) / 256), 256, 0, s>>> (zkey, (int) npix, *d_filled);
+  if (n)
+  {
+    size_t blocks = std::min<size_t> ((n + 255) / 256, (size_t) h->sm_count * 16);
+    k_org_zmin<<<(unsigned) blocks, 256, 0, s>>> (o, d_pts, n, stride, xyz_off, zkey);
+  }
+  k_org_gather<<<(unsigned) ((npix + 255) / 256), 256, 0, s>>> (o, d_pts, stride, xyz_off, rgba_off, zkey, *d_out, out_stride, out_rgba_off, *d_filled);
+  h->launches += n ? 3 : 2;
+  CK (cudaGetLastError ());
+  return B200TSDF_OK;
+}
+
+} // namespace
+
+int b200tsdf_organize (b200tsdf_t* h, const void* points, size_t n, size_t stride, int xyz_off, int rgba_off,
+                       const b200tsdf_organize_opts* opts, void* out, size_t out_stride, int out_rgba_off, int64_t* n_filled)
+{
+  if (!h || !out) return B200TSDF_EINVAL;
+  unsigned char* d_out = nullptr; unsigned long long* d_filled = nullptr;
+  int rc = organize_on_device (h, points, n, stride, xyz_off, rgba_off, opts, out_stride, out_rgba_off, &d_out, &d_filled);
+  if (rc) return rc;
+  size_t bytes = (size_t) h->cfg.image_width * h->cfg.image_height * out_stride;
+  unsigned long long filled = 0;
+  // bytes of a pixel that the layout does not name (padding) are zero in the result
+  CK (cudaMemcpyAsync (out, d_out, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK (cudaMemcpyAsync (&filled, d_filled, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK (cudaStreamSynchronize (h->stream));
+  h->d2h_bytes += (long long) bytes + 8;
+  if (n_filled) *n_filled = (int64_t) filled;
+  return B200TSDF_OK;
+}
+
+int b200tsdf_integrate_unorganized (b200tsdf_t* h, const void* points, size_t n, size_t stride, int xyz_off, int rgba_off,
+                                    const b200tsdf_organize_opts* opts, const double* pose)
+{
+  if (!h || !pose) return B200TSDF_EINVAL;
+  unsigned char* d_out = nullptr; unsigned long long* d_filled = nullptr;
+  // organized pixels are 16 bytes in HBM: x, y, z, then the colour bytes b,g,r,a
+  int rc = organize_on_device (h, points, n, stride, xyz_off, rgba_off, opts, 16, 12, &d_out, &d_filled);
+  if (rc) return rc;
+  return integrate_on_device (h, d_out, 16, 0, 12, h->cfg.image_width, h->cfg.image_height, pose);
+}
 
 int b200tsdf_sync (b200tsdf_t* h)
 {

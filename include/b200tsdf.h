@@ -87,6 +87,30 @@ int  b200tsdf_integrate_async (b200tsdf_t* h, const void* points, size_t stride,
                                int width, int height, const double* pose_c2w);
 int  b200tsdf_sync (b200tsdf_t* h);
 
+/* ---- unorganised clouds: the z-buffer re-organisation of the reference's `integrate` program ----
+ * (src/prog/integrate.cpp:548-635).  Per input point, in this order: scale by cloud_units (:550-559),
+ * turn (0,0,0) into NaN when zero_nans (:561-568), map world -> camera with world_to_camera when it is
+ * not NULL (pcl::transformPointCloud with poses[i].inverse(), :570-571; row-major 4x4, rows 0..2 used),
+ * project with the handle's intrinsics in float (reprojectPoint, :216-222), keep per pixel the point
+ * with the smallest z, the earliest such point on ties (:603-606).  Unfilled pixels are x=y=0, z=NaN,
+ * rgba=(0,0,0,255) (a default pcl::PointXYZRGBA with z overwritten, :597-598).  */
+typedef struct b200tsdf_organize_opts
+{
+  float   cloud_units;          /* 1 = metres                                   */
+  int32_t zero_nans;            /* --zero-nans                                  */
+  const double* world_to_camera;/* NULL unless --world (clouds in world frame)  */
+} b200tsdf_organize_opts;
+/* z-buffer `n` host points (stride / xyz_off / rgba_off as for b200tsdf_integrate) into an organized
+ * image_width x image_height cloud written to `out` (host; out_stride >= 16 bytes per pixel: xyz at 0,
+ * 1.0f at 12 when out_stride >= 32, colour bytes b,g,r,a at out_rgba_off or not written when -1).
+ * n_filled (may be NULL) receives the number of pixels that got a point. */
+int  b200tsdf_organize (b200tsdf_t* h, const void* points, size_t n, size_t stride, int xyz_off, int rgba_off,
+                        const b200tsdf_organize_opts* opts, void* out, size_t out_stride, int out_rgba_off,
+                        int64_t* n_filled);
+/* organise + integrateCloud without the organized cloud ever leaving HBM (integrate.cpp:582-635 + :673) */
+int  b200tsdf_integrate_unorganized (b200tsdf_t* h, const void* points, size_t n, size_t stride, int xyz_off,
+                                     int rgba_off, const b200tsdf_organize_opts* opts, const double* pose_c2w);
+
 /* getFxn / getGradient / getHessian (cpp:655-725) with mode 0, or the combined
  * getFxnAndGradient / getFxnGradientAndHessian (cpp:728-794) with mode 1.  what: bit0 value,
  * bit1 gradient (3 floats), bit2 hessian (9 floats, row-major).  ok[i] = the reference's bool.

@@ -53,8 +53,8 @@ def load(kind: str = "port") -> C.CDLL:
     if kind in _libs:
         return _libs[kind]
     path = PORT_LIB if kind == "port" else REF_LIB
-    if kind == "port" and not os.path.exists(path):
-        build()
+    if kind == "port":
+        build()                      # make: a no-op when the library is newer than its sources
     if not os.path.exists(path):
         raise FileNotFoundError(path)
     lib = C.CDLL(path)
@@ -74,8 +74,25 @@ def load(kind: str = "port") -> C.CDLL:
     lib.orc_voxel_center.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp]
     lib.orc_voxel_index.argtypes = [vp, C.c_float, C.c_float, C.c_float, vp]
     lib.orc_frustum_cull.argtypes = [vp, vp, vp]
+    if kind == "port":               # the program-side restatement (oracle/prog_oracle.cpp) exists in the port only
+        lib.orc_organize.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
+        lib.orc_organize.restype = C.c_int64
     _libs[kind] = lib
     return lib
+
+
+def organize(points: np.ndarray, intr, width: int, height: int, *, rgba_off: int = -1, cloud_units: float = 1.0,
+             zero_nans: bool = False, world_to_camera=None):
+    """integrate.cpp:548-607 — z-buffer an unorganised cloud ([n, k] float32 rows, xyz first, colour bytes at
+    rgba_off) into [height, width, 8] float32 rows in pcl::PointXYZRGBA layout.  Returns (organized, n_filled)."""
+    lib = load("port")
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    intr = np.asarray(intr, np.float32)
+    out = np.zeros((height, width, 8), np.float32)
+    tf = None if world_to_camera is None else np.ascontiguousarray(world_to_camera, dtype=np.float64)
+    filled = lib.orc_organize(_ptr(pts), pts.shape[0], pts.strides[0], 0, rgba_off, _ptr(intr), width, height,
+                              float(cloud_units), int(zero_nans), _ptr(tf), _ptr(out))
+    return out, int(filled)
 
 
 def _ptr(a):

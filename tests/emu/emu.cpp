@@ -7,6 +7,7 @@
 // directory and the per-node arithmetic before any GPU time is spent.  It is NOT part of the
 // product: libb200tsdf.so has no CPU path and nothing in cpu_tsdf_b200/ loads this library.
 #include "../../cpu_tsdf_b200/csrc/tsdf_core.cuh"
+#include "../../cpu_tsdf_b200/csrc/organize.cuh"
 #include "../../cpu_tsdf_b200/csrc/host_math.h"
 #include "../../cpu_tsdf_b200/csrc/params_setup.h"
 #include "../../oracle/mc_tables.h"
@@ -248,3 +249,35 @@ int emu_frustum_cull (const Emu* e, const double* pose, uint8_t* mask)
 }
 
 } // extern "C"
+
+// organize.cuh driven serially in REVERSE point order (the device order is arbitrary): the result must
+// not depend on it
+extern "C" long long emu_organize (const void* points, size_t n, size_t stride, int xyz_off, int rgba_off, const float* intr,
+                                   int width, int height, float cloud_units, int zero_nans, const double* tf,
+                                   void* out, size_t out_stride, int out_rgba_off)
+{
+  OrgParams o{};
+  o.fx = intr[0]; o.fy = intr[1]; o.cx = intr[2]; o.cy = intr[3]; o.width = width; o.height = height;
+  o.cloud_units = cloud_units; o.zero_nans = zero_nans; o.has_tf = tf != nullptr;
+  if (tf) for (int i = 0; i < 12; ++i) o.tf[i] = tf[i];
+  const unsigned char* pts = (const unsigned char*) points;
+  size_t npix = (size_t) width * height;
+  std::vector<unsigned long long> zkey (npix, ~0ull);
+  for (size_t j = n; j-- > 0;)
+  {
+    float x, y, z;
+    org_load (pts, stride, xyz_off, j, x, y, z);
+    org_prepare (o, x, y, z);
+    int pix = org_pixel (o, x, y, z);
+    if (pix < 0) continue;
+    zkey[pix] = std::min (zkey[pix], org_key (z, (unsigned int) j));
+  }
+  long long filled = 0;
+  for (size_t i = 0; i < npix; ++i)
+  {
+    filled += zkey[i] != ~0ull;
+    org_emit (o, pts, stride, xyz_off, rgba_off, zkey[i], (unsigned char*) out + i * out_stride, out_stride, out_rgba_off);
+  }
+  return filled;
+}
+

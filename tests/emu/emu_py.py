@@ -17,7 +17,7 @@ CORE = os.path.join(HERE, "..", "..", "cpu_tsdf_b200", "csrc")
 
 
 def build():
-    deps = [SRC] + [os.path.join(CORE, f) for f in ("tsdf_core.cuh", "host_math.h", "params_setup.h")]
+    deps = [SRC] + [os.path.join(CORE, f) for f in ("tsdf_core.cuh", "organize.cuh", "host_math.h", "params_setup.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -44,6 +44,8 @@ def load():
         lib.emu_mesh.argtypes = [vp, C.c_float, C.c_int, C.POINTER(vp), C.POINTER(vp)]; lib.emu_mesh.restype = C.c_longlong
         lib.emu_levels.argtypes = [vp, vp]
         lib.emu_frustum_cull.argtypes = [vp, vp, vp]
+        lib.emu_organize.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, C.c_size_t, C.c_int]
+        lib.emu_organize.restype = C.c_longlong
         _lib = lib
     return _lib
 
@@ -149,3 +151,15 @@ class EmuVolume:
         pose = np.ascontiguousarray(pose, dtype=np.float64)
         kept = self.lib.emu_frustum_cull(self.h, _ptr(pose), _ptr(mask))
         return mask, kept
+
+
+def organize(points, intr, width, height, *, rgba_off=-1, cloud_units=1.0, zero_nans=False, world_to_camera=None,
+             out_stride=32, out_rgba_off=16):
+    lib = load()
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    intr = np.asarray(intr, np.float32)
+    out = np.full((height, width, out_stride // 4), 7.0, np.float32)       # pre-filled: padding must come back zero
+    tf = None if world_to_camera is None else np.ascontiguousarray(world_to_camera, dtype=np.float64)
+    filled = lib.emu_organize(_ptr(pts), pts.shape[0], pts.strides[0], 0, rgba_off, _ptr(intr), width, height,
+                              float(cloud_units), int(zero_nans), _ptr(tf), _ptr(out), out_stride, out_rgba_off)
+    return out, int(filled)
