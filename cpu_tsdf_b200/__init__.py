@@ -73,6 +73,7 @@ EXPORTS = [
     "b200tsdf_free", "b200tsdf_save", "b200tsdf_load", "b200tsdf_export_shard", "b200tsdf_import_shard", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
     "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_frustum_cull",
     "b200tsdf_profile_begin", "b200tsdf_profile_end",
+    "b200tsdf_mesh_flatten", "b200tsdf_mesh_cleanup", "b200tsdf_mesh_free", "b200tsdf_meshpost_last_error",
 ]
 
 _lib = None
@@ -100,6 +101,11 @@ def load_library() -> C.CDLL:
     lib.b200tsdf_integrate_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_integrate_async.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_sync.argtypes = [vp]
+    szp = C.POINTER(C.c_size_t)
+    lib.b200tsdf_mesh_flatten.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_float, C.POINTER(vp), szp, C.POINTER(vp), szp]
+    lib.b200tsdf_mesh_cleanup.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_float, C.c_int, C.POINTER(vp), szp, C.POINTER(vp), szp]
+    lib.b200tsdf_mesh_free.argtypes = [vp]
+    lib.b200tsdf_meshpost_last_error.restype = C.c_char_p
     lib.b200tsdf_organize.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(OrganizeOpts), vp, C.c_size_t, C.c_int, C.POINTER(C.c_int64)]
     lib.b200tsdf_integrate_unorganized.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(OrganizeOpts), vp]
     lib.b200tsdf_query.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
@@ -458,3 +464,32 @@ class MarchingCubesTSDFOctree:
                 C.memmove(rgb.ctypes.data, pc.value, nv * 3)
         polys = np.arange(nv, dtype=np.int32).reshape(-1, 3)
         return verts, rgb, polys
+
+
+# ---- mesh post-processing of the reference's `integrate` program (src/prog/integrate.cpp:103-214) ----------
+def _meshpost(fn_name, verts, tris, *args, device=0):
+    lib = load_library()
+    verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    tris = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+    ov, ot = C.c_void_p(), C.c_void_p()
+    nv, nt = C.c_size_t(0), C.c_size_t(0)
+    rc = getattr(lib, fn_name)(device, _ptr(verts), len(verts), _ptr(tris), len(tris), *args,
+                               C.byref(ov), C.byref(nv), C.byref(ot), C.byref(nt))
+    if rc != 0:
+        raise B200Error(f"{fn_name}: error {rc}: {lib.b200tsdf_meshpost_last_error().decode()}")
+    try:
+        v = np.ctypeslib.as_array(C.cast(ov, C.POINTER(C.c_float)), (max(nv.value, 1) * 3,))[:nv.value * 3].reshape(-1, 3).copy()
+        t = np.ctypeslib.as_array(C.cast(ot, C.POINTER(C.c_int32)), (max(nt.value, 1) * 3,))[:nt.value * 3].reshape(-1, 3).copy()
+    finally:
+        lib.b200tsdf_mesh_free(ov); lib.b200tsdf_mesh_free(ot)
+    return v, t
+
+
+def flattenVertices(verts, tris, min_dist: float = 0.0001, device: int = 0):
+    """integrate.cpp:103-150: weld vertices closer than min_dist, drop degenerate faces.  -> (verts [n,3], tris [m,3])"""
+    return _meshpost("b200tsdf_mesh_flatten", verts, tris, C.c_float(min_dist), device=device)
+
+
+def cleanupMesh(verts, tris, face_dist: float = 0.02, min_neighbors: int = 5, device: int = 0):
+    """integrate.cpp:152-214: remove face clusters of at most min_neighbors faces and the vertices left unused."""
+    return _meshpost("b200tsdf_mesh_cleanup", verts, tris, C.c_float(face_dist), int(min_neighbors), device=device)

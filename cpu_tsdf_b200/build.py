@@ -8,14 +8,18 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200tsdf.so")
-SOURCES = ["engine.cu"]
-HEADERS = ["tsdf_core.cuh", "mc_tables.cuh", "host_math.h", "params_setup.h", "brick_kernels.cuh"]
+# source -> headers it includes (csrc/), for incremental rebuilds
+SOURCES = {
+    "engine.cu": ["tsdf_core.cuh", "mc_tables.cuh", "host_math.h", "params_setup.h", "brick_kernels.cuh", "organize.cuh"],
+    "meshpost.cu": ["tsdf_core.cuh", "meshpost_core.cuh"],
+}
+OBJ = os.path.join(CSRC, "_obj")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # every float expression must round exactly as the reference's: no FMA contraction anywhere
     "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
-    "-shared", "-Xptxas", "-v",
+    "-Xptxas", "-v",
 ]
 
 
@@ -26,25 +30,50 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "b200tsdf.h")]
+    t = os.path.getmtime(target)
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def _deps(src: str) -> list[str]:
+    return [os.path.join(CSRC, f) for f in [src] + SOURCES[src]] + [os.path.join(HERE, "..", "include", "b200tsdf.h"), __file__]
+
+
+def needs_build() -> bool:
+    return any(_stale(LIB, _deps(s)) for s in SOURCES)
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -c per source (only the stale ones, in parallel), then one link into libb200tsdf.so."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    ccbin = ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _stale(obj, _deps(src)):
+            cmd = [nvcc_path()] + NVCC_FLAGS + ccbin + ["-c", "-o", obj, os.path.join(CSRC, src)]
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    out = ""
+    failed = False
+    for cmd, pr in jobs:
+        o, _ = pr.communicate()
+        out += " ".join(cmd) + "\n" + o
+        failed |= pr.returncode != 0
+    if not failed:
+        cmd = [nvcc_path(), "-shared"] + ccbin + ["-o", LIB] + [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        out += " ".join(cmd) + "\n" + r.stdout + r.stderr
+        failed = r.returncode != 0
+    # keep the ptxas -v output of every object in the log, also of those that were not recompiled this time
     log = os.path.join(HERE, "build.log")
-    with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    with open(log, "w" if force or len(jobs) == len(SOURCES) else "a") as f:
+        f.write(out)
     if verbose:
-        print(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+        print(out)
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + out[-8000:])
     return LIB

@@ -132,6 +132,22 @@ int  b200tsdf_render (b200tsdf_t* h, const double* pose_c2w, int downsample, voi
 int  b200tsdf_mesh (b200tsdf_t* h, float w_min, int color_mode, float** verts, uint8_t** rgb, size_t* nverts);
 void b200tsdf_free (void* p);
 
+/* ---- mesh post-processing of the reference's `integrate` program (no volume handle needed) ----------
+ * Meshes are indexed: nverts xyz triples + ntris index triples (a marching-cubes soup is tris = 0,1,2,...).
+ * Outputs are malloc'ed by the library; release each with b200tsdf_mesh_free.  Vertex colours are not
+ * carried: the reference converts the mesh cloud to pcl::PointXYZ in both functions (integrate.cpp:106, 186).
+ * flattenVertices (src/prog/integrate.cpp:103-150): vertices closer than min_dist are welded (in index
+ * order, as the reference's sweep does), faces that become degenerate are dropped. */
+int  b200tsdf_mesh_flatten (int device, const float* verts, size_t nverts, const int32_t* tris, size_t ntris, float min_dist,
+                            float** out_verts, size_t* out_nverts, int32_t** out_tris, size_t* out_ntris);
+/* cleanupMesh (src/prog/integrate.cpp:152-214): faces whose centroids form clusters (cluster tolerance
+ * face_dist) of at most min_neighbors faces are removed, then the vertices no face uses. */
+int  b200tsdf_mesh_cleanup (int device, const float* verts, size_t nverts, const int32_t* tris, size_t ntris,
+                            float face_dist, int min_neighbors,
+                            float** out_verts, size_t* out_nverts, int32_t** out_tris, size_t* out_ntris);
+void b200tsdf_mesh_free (void* p);
+const char* b200tsdf_meshpost_last_error (void);   /* thread-local message of the last failed call above */
+
 /* TSDFVolumeOctree::save (cpp:222-245): reference-compatible .vol */
 int  b200tsdf_save (b200tsdf_t* h, const char* path);
 

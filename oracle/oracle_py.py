@@ -77,6 +77,8 @@ def load(kind: str = "port") -> C.CDLL:
     if kind == "port":               # the program-side restatement (oracle/prog_oracle.cpp) exists in the port only
         lib.orc_organize.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
         lib.orc_organize.restype = C.c_int64
+        lib.orc_flatten_vertices.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_float, vp, vp, vp, vp]
+        lib.orc_cleanup_mesh.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_float, C.c_int, vp, vp, vp, vp]
     _libs[kind] = lib
     return lib
 
@@ -200,3 +202,21 @@ class OracleVolume:
         pose = np.ascontiguousarray(pose, dtype=np.float64)
         kept = self.lib.orc_frustum_cull(self.h, _ptr(pose), _ptr(mask))
         return mask, kept
+
+
+def _mesh_call(fn, verts, tris, *args):
+    verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3); tris = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+    ov = np.zeros_like(verts); ot = np.zeros_like(tris)
+    nv = C.c_size_t(0); nt = C.c_size_t(0)
+    fn(_ptr(verts), len(verts), _ptr(tris), len(tris), *args, _ptr(ov), C.byref(nv), _ptr(ot), C.byref(nt))
+    return ov[:nv.value].copy(), ot[:nt.value].copy()
+
+
+def flatten_vertices(verts, tris, min_dist=0.0001):
+    """flattenVertices, integrate.cpp:103-150 -> (vertices [n,3], triangles [m,3])"""
+    return _mesh_call(load("port").orc_flatten_vertices, verts, tris, C.c_float(min_dist))
+
+
+def cleanup_mesh(verts, tris, face_dist=0.02, min_neighbors=5):
+    """cleanupMesh, integrate.cpp:152-214"""
+    return _mesh_call(load("port").orc_cleanup_mesh, verts, tris, C.c_float(face_dist), int(min_neighbors))

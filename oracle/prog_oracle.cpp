@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <limits>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -26,9 +28,148 @@ inline int to_int (float v)
   return static_cast<int> (v);
 }
 
+// Stand-in for pcl::search::KdTree<PointT>::radiusSearch (FLANN kd-tree, absent here): returns the
+// indices j != query with squared distance < radius^2.  Conventions [recalled]: FLANN's L2_Simple<float>
+// accumulates (dx*dx + dy*dy) + dz*dz in float; RadiusResultSet keeps dist < radius^2 where
+// radius^2 = float (double (radius) * double (radius)) (KdTreeFLANN::radiusSearch).  The query point itself
+// (distance 0, returned first by the sorted search and skipped by the callers' `j = 1` / processed flag) is
+// left out.  A uniform bucket grid is only the search structure; membership is decided by the test above.
+struct RadiusSearch
+{
+  const float* pts; size_t n; float cell, r2;
+  std::unordered_map<uint64_t, std::vector<int> > buckets;
+  static int64_t c1 (float x, float cell) { return static_cast<int64_t> (std::floor (static_cast<double> (x) / cell)); }
+  static uint64_t key (int64_t x, int64_t y, int64_t z)
+  { return (static_cast<uint64_t> (x & 0x1fffff) << 42) | (static_cast<uint64_t> (y & 0x1fffff) << 21) | static_cast<uint64_t> (z & 0x1fffff); }
+  RadiusSearch (const float* p, size_t n_, float radius) : pts (p), n (n_)
+  {
+    cell = std::max (radius * 1.01f, 1e-6f);
+    r2 = static_cast<float> (static_cast<double> (radius) * static_cast<double> (radius));
+    buckets.reserve (n * 2);
+    for (size_t i = 0; i < n; ++i)
+      buckets[key (c1 (p[3 * i], cell), c1 (p[3 * i + 1], cell), c1 (p[3 * i + 2], cell))].push_back (static_cast<int> (i));
+  }
+  void search (int i, std::vector<int>& out) const
+  {
+    out.clear ();
+    const float* q = pts + 3 * static_cast<size_t> (i);
+    int64_t cx = c1 (q[0], cell), cy = c1 (q[1], cell), cz = c1 (q[2], cell);
+    for (int64_t x = cx - 1; x <= cx + 1; ++x)
+      for (int64_t y = cy - 1; y <= cy + 1; ++y)
+        for (int64_t z = cz - 1; z <= cz + 1; ++z)
+        {
+          auto it = buckets.find (key (x, y, z));
+          if (it == buckets.end ()) continue;
+          for (int j : it->second)
+          {
+            if (j == i) continue;
+            const float* b = pts + 3 * static_cast<size_t> (j);
+            float dx = q[0] - b[0], dy = q[1] - b[1], dz = q[2] - b[2];
+            float d = dx * dx + dy * dy + dz * dz;
+            if (d < r2) out.push_back (j);
+          }
+        }
+  }
+};
+
 } // namespace
 
 extern "C" {
+
+// flattenVertices, integrate.cpp:103-150.  out_verts has room for nverts xyz, out_tris for ntris triples.
+void orc_flatten_vertices (const float* verts, size_t nverts, const int32_t* tris, size_t ntris, float min_dist,
+                           float* out_verts, size_t* out_nverts, int32_t* out_tris, size_t* out_ntris)
+{
+  RadiusSearch vert_tree (verts, nverts, min_dist);
+  // :109-127 Find duplicates
+  std::vector<int> vertex_remap (nverts, -1);
+  int idx = 0;
+  std::vector<int> neighbors;
+  size_t nnew = 0;
+  for (size_t i = 0; i < nverts; i++)
+  {
+    if (vertex_remap[i] >= 0) continue;
+    vertex_remap[i] = idx;
+    vert_tree.search (static_cast<int> (i), neighbors);
+    // :121-125: every returned neighbour passes `dists[j] < min_dist` (a squared distance below radius^2 <= 1e-8
+    // compared with 1e-4), so all of them are (re)assigned
+    for (size_t j = 0; j < neighbors.size (); j++) vertex_remap[neighbors[j]] = idx;
+    out_verts[3 * nnew] = verts[3 * i]; out_verts[3 * nnew + 1] = verts[3 * i + 1]; out_verts[3 * nnew + 2] = verts[3 * i + 2];
+    ++nnew;
+    idx++;
+  }
+  // :128-147
+  size_t face_idx = 0;
+  for (size_t i = 0; i < ntris; i++)
+  {
+    int32_t v[3];
+    for (int j = 0; j < 3; j++) v[j] = vertex_remap[tris[3 * i + j]];
+    if (v[0] == v[1] || v[1] == v[2] || v[2] == v[0]) continue;              // "Degenerate face"
+    out_tris[3 * face_idx] = v[0]; out_tris[3 * face_idx + 1] = v[1]; out_tris[3 * face_idx + 2] = v[2];
+    ++face_idx;
+  }
+  *out_nverts = nnew; *out_ntris = face_idx;
+}
+
+// cleanupMesh, integrate.cpp:152-214, with pcl::EuclideanClusterExtraction (pcl/segmentation/impl/
+// extract_clusters.hpp, extractEuclideanClusters [recalled]: breadth-first growth over radiusSearch, clusters
+// with min_pts (default 1) <= size <= max_pts are returned).
+void orc_cleanup_mesh (const float* verts, size_t nverts, const int32_t* tris, size_t ntris, float face_dist, int min_neighbors,
+                       float* out_verts, size_t* out_nverts, int32_t* out_tris, size_t* out_ntris)
+{
+  // meshToFaceCloud, :70-101: p_new.getVector3fMap () = (v0 + v1 + v2) / 3.  (Vector3f arithmetic: float)
+  std::vector<float> faces (3 * ntris);
+  for (size_t i = 0; i < ntris; ++i)
+    for (int k = 0; k < 3; ++k)
+      faces[3 * i + k] = ((verts[3 * tris[3 * i] + k] + verts[3 * tris[3 * i + 1] + k]) + verts[3 * tris[3 * i + 2] + k]) / 3.f;
+  RadiusSearch face_tree (faces.data (), ntris, face_dist);
+  std::vector<std::vector<int> > clusters;
+  {
+    std::vector<bool> processed (ntris, false);
+    std::vector<int> nn;
+    for (size_t i = 0; i < ntris; ++i)
+    {
+      if (processed[i]) continue;
+      std::vector<int> seed_queue;
+      size_t sq_idx = 0;
+      seed_queue.push_back (static_cast<int> (i));
+      processed[i] = true;
+      while (sq_idx < seed_queue.size ())
+      {
+        face_tree.search (seed_queue[sq_idx], nn);
+        for (int j : nn)
+        {
+          if (processed[j]) continue;
+          seed_queue.push_back (j);
+          processed[j] = true;
+        }
+        sq_idx++;
+      }
+      if (seed_queue.size () >= 1 && seed_queue.size () <= static_cast<size_t> (min_neighbors)) clusters.push_back (seed_queue);
+    }
+  }
+  // :170-183
+  std::vector<size_t> faces_to_remove;
+  for (auto& c : clusters) for (int j : c) faces_to_remove.push_back (static_cast<size_t> (j));
+  std::sort (faces_to_remove.begin (), faces_to_remove.end ());
+  std::vector<bool> erased (ntris, false);
+  for (size_t f : faces_to_remove) erased[f] = true;                           // polygons.erase, back to front
+  std::vector<int32_t> polys;
+  for (size_t i = 0; i < ntris; ++i) if (!erased[i]) { polys.push_back (tris[3 * i]); polys.push_back (tris[3 * i + 1]); polys.push_back (tris[3 * i + 2]); }
+  // :184-213 Remove all vertices with no face
+  std::vector<bool> has_face (nverts, false);
+  for (int32_t v : polys) has_face[v] = true;
+  std::vector<size_t> get_new_idx (nverts);
+  size_t cur_idx = 0;
+  for (size_t i = 0; i < nverts; i++)
+    if (has_face[i])
+    {
+      out_verts[3 * cur_idx] = verts[3 * i]; out_verts[3 * cur_idx + 1] = verts[3 * i + 1]; out_verts[3 * cur_idx + 2] = verts[3 * i + 2];
+      get_new_idx[i] = cur_idx++;
+    }
+  for (size_t i = 0; i < polys.size (); ++i) out_tris[i] = static_cast<int32_t> (get_new_idx[polys[i]]);
+  *out_nverts = cur_idx; *out_ntris = polys.size () / 3;
+}
 
 // integrate.cpp:548-607 for one cloud.  intr = {fx, fy, cx, cy} as the program's float globals (:63-68).
 // out: width*height pcl::PointXYZRGBA (32 bytes each).  Returns the number of pixels that received a point.

@@ -8,6 +8,7 @@
 // product: libb200tsdf.so has no CPU path and nothing in cpu_tsdf_b200/ loads this library.
 #include "../../cpu_tsdf_b200/csrc/tsdf_core.cuh"
 #include "../../cpu_tsdf_b200/csrc/organize.cuh"
+#include "../../cpu_tsdf_b200/csrc/meshpost_core.cuh"
 #include "../../cpu_tsdf_b200/csrc/host_math.h"
 #include "../../cpu_tsdf_b200/csrc/params_setup.h"
 #include "../../oracle/mc_tables.h"
@@ -281,3 +282,77 @@ extern "C" long long emu_organize (const void* points, size_t n, size_t stride, 
   return filled;
 }
 
+
+// ---- meshpost_core.cuh driven serially, every per-element loop in REVERSE order -------------------------
+namespace {
+struct HostGrid
+{
+  std::vector<uint64_t> keys; std::vector<int> head, next; PointGrid g{};
+  HostGrid (const float* pts, int n, double cell)
+  {
+    size_t slots = 1024; while (slots < 2 * (size_t) n) slots <<= 1;
+    keys.assign (slots, GRID_EMPTY); head.assign (slots, -1); next.assign (std::max (n, 1), -1);
+    g.keys = keys.data (); g.head = head.data (); g.next = next.data (); g.mask = (uint32_t) (slots - 1); g.inv_cell = 1.0 / cell; g.pts = pts;
+    for (int i = n; i-- > 0;) grid_insert (g, i);
+  }
+};
+}
+
+extern "C" void emu_mesh_flatten (const float* verts, size_t nverts, const int32_t* tris, size_t ntris, float min_dist,
+                                  float* out_verts, size_t* out_nverts, int32_t* out_tris, size_t* out_ntris, int* rounds_out)
+{
+  int nv = (int) nverts;
+  const float r2 = (float) ((double) min_dist * (double) min_dist);
+  HostGrid G (verts, nv, std::max ((double) min_dist * 1.001, 1e-7));
+  std::vector<unsigned char> state (std::max (nv, 1), FV_UNDECIDED);
+  int rounds = 0;
+  for (bool again = true; again; ++rounds)
+  {
+    again = false;
+    for (int i = nv; i-- > 0;) again |= fv_round (G.g, r2, state.data (), i);
+  }
+  if (rounds_out) *rounds_out = rounds;
+  std::vector<int> rep (nv), rank (nv);
+  size_t k = 0;
+  for (int i = 0; i < nv; ++i) { rank[i] = (int) k; if (state[i] == FV_KEPT) { for (int c = 0; c < 3; ++c) out_verts[3 * k + c] = verts[3 * (size_t) i + c]; ++k; } }
+  for (int i = nv; i-- > 0;) rep[i] = fv_target (G.g, r2, state.data (), i);
+  size_t f = 0;
+  for (size_t t = 0; t < ntris; ++t)
+  {
+    int a = rank[rep[tris[3 * t]]], b = rank[rep[tris[3 * t + 1]]], c = rank[rep[tris[3 * t + 2]]];
+    if (a == b || b == c || c == a) continue;
+    out_tris[3 * f] = a; out_tris[3 * f + 1] = b; out_tris[3 * f + 2] = c; ++f;
+  }
+  *out_nverts = k; *out_ntris = f;
+}
+
+extern "C" void emu_mesh_cleanup (const float* verts, size_t nverts, const int32_t* tris, size_t ntris, float face_dist, int K,
+                                  float* out_verts, size_t* out_nverts, int32_t* out_tris, size_t* out_ntris)
+{
+  int nt = (int) ntris;
+  const float r2 = (float) ((double) face_dist * (double) face_dist);
+  std::vector<float> cent (3 * std::max<size_t> (ntris, 1));
+  for (int t = nt; t-- > 0;) face_centroid (verts, tris + 3 * (size_t) t, cent.data () + 3 * (size_t) t);
+  HostGrid G (cent.data (), nt, std::max ((double) face_dist * 1.001, 1e-7));
+  std::vector<int> cnt (nt), nb ((size_t) std::max (nt, 1) * (CM_MAX_K - 1)), parent (nt), touches (nt, 0), size (nt, 0), has_big (nt, 0), keep (nt);
+  for (int t = nt; t-- > 0;) { cnt[t] = cm_count (G.g, r2, K, t, nb.data ()); parent[t] = t; }
+  for (int t = nt; t-- > 0;)
+  {
+    if (cnt[t] >= K) continue;
+    for (int k = 0; k < cnt[t]; ++k) { int j = nb[(size_t) t * (CM_MAX_K - 1) + k]; if (cnt[j] >= K) touches[t] = 1; else uf_union (parent.data (), t, j); }
+  }
+  for (int t = nt; t-- > 0;) if (cnt[t] < K) { int r = uf_find (parent.data (), t); size[r]++; if (touches[t]) has_big[r] = 1; }
+  for (int t = 0; t < nt; ++t)
+  {
+    bool remove = false;
+    if (cnt[t] < K) { int r = uf_find (parent.data (), t); remove = !has_big[r] && size[r] <= K; }
+    keep[t] = !remove;
+  }
+  std::vector<int> used (nverts, 0), vrank (nverts, 0);
+  for (int t = 0; t < nt; ++t) if (keep[t]) for (int c = 0; c < 3; ++c) used[tris[3 * (size_t) t + c]] = 1;
+  size_t k = 0;
+  for (size_t i = 0; i < nverts; ++i) { vrank[i] = (int) k; if (used[i]) { for (int c = 0; c < 3; ++c) out_verts[3 * k + c] = verts[3 * i + c]; ++k; } }
+  size_t f = 0;
+  for (int t = 0; t < nt; ++t) if (keep[t]) { for (int c = 0; c < 3; ++c) out_tris[3 * f + c] = vrank[tris[3 * (size_t) t + c]]; ++f; }
+  *out_nverts = k; *out_ntris = f;
+}

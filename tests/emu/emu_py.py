@@ -17,7 +17,7 @@ CORE = os.path.join(HERE, "..", "..", "cpu_tsdf_b200", "csrc")
 
 
 def build():
-    deps = [SRC] + [os.path.join(CORE, f) for f in ("tsdf_core.cuh", "organize.cuh", "host_math.h", "params_setup.h")]
+    deps = [SRC] + [os.path.join(CORE, f) for f in ("tsdf_core.cuh", "organize.cuh", "meshpost_core.cuh", "host_math.h", "params_setup.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -46,6 +46,8 @@ def load():
         lib.emu_frustum_cull.argtypes = [vp, vp, vp]
         lib.emu_organize.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, C.c_size_t, C.c_int]
         lib.emu_organize.restype = C.c_longlong
+        lib.emu_mesh_flatten.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_float, vp, vp, vp, vp, vp]
+        lib.emu_mesh_cleanup.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_float, C.c_int, vp, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -163,3 +165,21 @@ def organize(points, intr, width, height, *, rgba_off=-1, cloud_units=1.0, zero_
     filled = lib.emu_organize(_ptr(pts), pts.shape[0], pts.strides[0], 0, rgba_off, _ptr(intr), width, height,
                               float(cloud_units), int(zero_nans), _ptr(tf), _ptr(out), out_stride, out_rgba_off)
     return out, int(filled)
+
+
+def _mesh_call(fn, verts, tris, *args, extra=()):
+    verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3); tris = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+    ov = np.zeros_like(verts); ot = np.zeros_like(tris)
+    nv = C.c_size_t(0); nt = C.c_size_t(0)
+    fn(_ptr(verts), len(verts), _ptr(tris), len(tris), *args, _ptr(ov), C.byref(nv), _ptr(ot), C.byref(nt), *extra)
+    return ov[:nv.value].copy(), ot[:nt.value].copy()
+
+
+def flatten_vertices(verts, tris, min_dist=0.0001, return_rounds=False):
+    rounds = C.c_int(0)
+    out = _mesh_call(load().emu_mesh_flatten, verts, tris, C.c_float(min_dist), extra=(C.byref(rounds),))
+    return out + (rounds.value,) if return_rounds else out
+
+
+def cleanup_mesh(verts, tris, face_dist=0.02, min_neighbors=5):
+    return _mesh_call(load().emu_mesh_cleanup, verts, tris, C.c_float(face_dist), int(min_neighbors))

@@ -96,7 +96,7 @@ def test_cuda_organize_matches_the_restatement():
 @pytest.mark.gpu
 def test_unorganized_integration_equals_organized_integration_of_the_oracle():
     import cpu_tsdf_b200 as pkg
-    o = oracle_py.OracleVolume(**CFG_256, integrate_color=1)
+    o = oracle_py.OracleVolume(**CFG_256, integrate_color=1); o.reset()
     v = pkg.TSDFVolumeOctree(device=0)
     v.setResolution(256, 256, 256); v.setGridSize(3, 3, 3); v.setCameraIntrinsics(525, 525, CAM.cx, CAM.cy)
     v.setIntegrateColor(True); v.reset()
