@@ -77,3 +77,32 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed:\n" + out[-8000:])
     return LIB
+
+
+# ---- host programs above the C ABI (the reference's src/prog equivalents) ---------------------------------------
+PROG = os.path.join(HERE, "prog")
+BIN = os.path.join(HERE, "bin")
+PROGRAMS = {                       # name -> needs libb200tsdf
+    "b200_integrate": True, "b200_tsdf2mesh": True, "b200_pcd_convert": False,
+}
+
+
+def build_programs(force: bool = False) -> list[str]:
+    """g++ the programs under prog/ into bin/ (rpath $ORIGIN/.. so they find libb200tsdf.so in-tree)."""
+    os.makedirs(BIN, exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    inc = os.path.join(HERE, "..", "include")
+    hdrs = [os.path.join(PROG, f) for f in os.listdir(PROG) if f.endswith(".h")] + \
+           [os.path.join(inc, "b200tsdf.h"), os.path.join(inc, "cpu_tsdf_b200", "tsdf_volume_octree.h"), os.path.join(CSRC, "host_math.h")]
+    out = []
+    for name, needs_lib in PROGRAMS.items():
+        src, exe = os.path.join(PROG, name + ".cpp"), os.path.join(BIN, name)
+        if force or _stale(exe, [src] + hdrs + ([LIB] if needs_lib else [])):
+            cmd = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-I" + inc, src, "-o", exe]
+            if needs_lib:
+                cmd += ["-L" + HERE, "-lb200tsdf", "-Wl,-rpath,$ORIGIN/.."]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+        out.append(exe)
+    return out

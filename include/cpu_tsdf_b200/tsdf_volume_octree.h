@@ -139,6 +139,23 @@ public:
     return status_ == 0;
   }
 
+  // The front end of the reference's `integrate` program for unorganised clouds (src/prog/integrate.cpp:548-635,
+  // 673): scale / zero->NaN / world->camera / z-buffer onto the image grid / integrateCloud, all on the device.
+  // `points`: n records of `stride` bytes, xyz at xyz_off, colour bytes b,g,r,a at rgba_off (or -1).
+  bool integrateUnorganizedCloud (const void* points, std::size_t n, std::size_t stride, int xyz_off, int rgba_off,
+                                  const Affine3d& trans = Affine3d::Identity (), float cloud_units = 1.f, bool zero_nans = false,
+                                  const Affine3d* world_to_camera = nullptr)
+  {
+    if (!h_) return false;
+    double m[16], w2c[16];
+    detail::pose_rows (trans, m);
+    b200tsdf_organize_opts opts;
+    opts.cloud_units = cloud_units; opts.zero_nans = zero_nans ? 1 : 0; opts.world_to_camera = nullptr;
+    if (world_to_camera) { detail::pose_rows (*world_to_camera, w2c); opts.world_to_camera = w2c; }
+    status_ = b200tsdf_integrate_unorganized (h_, points, n, stride, xyz_off, rgba_off, &opts, m);
+    return status_ == 0;
+  }
+
   bool getFxn (const PointXYZ& pt, float& val) const                                               // cpp:655-672
   { std::uint8_t ok = 0; float p[3] = { pt.x, pt.y, pt.z }; b200tsdf_query (h_, p, 1, 1, 0, &val, nullptr, nullptr, &ok); return ok != 0; }
   bool getGradient (const PointXYZ& pt, float grad[3]) const                                       // cpp:681-700
@@ -238,5 +255,33 @@ private:
   bool color_by_confidence_ = false, color_by_rgb_ = false;
   float w_min_ = 2.5f;
 };
+
+#ifndef B200TSDF_WITH_PCL
+// The mesh post-processing of the reference's `integrate` program, on the GPU.  Like the reference's versions they
+// rebuild the mesh cloud as plain XYZ: vertex colours do not survive (src/prog/integrate.cpp:106, 149, 186, 213).
+namespace detail
+{
+  template <typename Fn> inline bool meshpost (TriangleSoup& mesh, Fn&& call)
+  {
+    float* v = nullptr; std::int32_t* t = nullptr; std::size_t nv = 0, nt = 0;
+    if (call (mesh.xyz.data (), mesh.xyz.size () / 3, mesh.polygons.data (), mesh.polygons.size () / 3, &v, &nv, &t, &nt) != 0) return false;
+    mesh.xyz.assign (v, v + 3 * nv); mesh.polygons.assign (t, t + 3 * nt); mesh.rgb.clear ();
+    b200tsdf_mesh_free (v); b200tsdf_mesh_free (t);
+    return true;
+  }
+}
+// flattenVertices (src/prog/integrate.cpp:103-150)
+inline bool flattenVertices (TriangleSoup& mesh, float min_dist = 0.0001f, int device = 0)
+{
+  return detail::meshpost (mesh, [&] (const float* v, std::size_t nv, const std::int32_t* t, std::size_t nt, float** ov, std::size_t* onv, std::int32_t** ot, std::size_t* ont)
+                           { return b200tsdf_mesh_flatten (device, v, nv, t, nt, min_dist, ov, onv, ot, ont); });
+}
+// cleanupMesh (src/prog/integrate.cpp:152-214)
+inline bool cleanupMesh (TriangleSoup& mesh, float face_dist = 0.02f, int min_neighbors = 5, int device = 0)
+{
+  return detail::meshpost (mesh, [&] (const float* v, std::size_t nv, const std::int32_t* t, std::size_t nt, float** ov, std::size_t* onv, std::int32_t** ot, std::size_t* ont)
+                           { return b200tsdf_mesh_cleanup (device, v, nv, t, nt, face_dist, min_neighbors, ov, onv, ot, ont); });
+}
+#endif
 
 } // namespace cpu_tsdf_b200
