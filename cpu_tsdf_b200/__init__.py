@@ -289,7 +289,7 @@ class TSDFVolumeOctree:
         out = np.empty((H, W, 8), np.float32)
         opts, _keep = self._org_opts(cloud_units, zero_nans, world_to_camera)
         filled = C.c_int64(0)
-        self._check(self._lib.b200tsdf_organize(self._h, _ptr(pts), pts.shape[0], pts.strides[0], 0, 16 if pts.shape[1] >= 5 else -1,
+        self._check(self._lib.b200tsdf_organize(self._h, _ptr(pts), pts.shape[0], pts.shape[1] * 4, 0, 16 if pts.shape[1] >= 5 else -1,
                                                 C.byref(opts), _ptr(out), 32, 16, C.byref(filled)))
         return out, int(filled.value)
 
@@ -302,7 +302,7 @@ class TSDFVolumeOctree:
             raise ValueError("points must be [n, >=3] float32")
         opts, _keep = self._org_opts(cloud_units, zero_nans, world_to_camera)
         pose = _pose(trans)
-        self._check(self._lib.b200tsdf_integrate_unorganized(self._h, _ptr(pts), pts.shape[0], pts.strides[0], 0,
+        self._check(self._lib.b200tsdf_integrate_unorganized(self._h, _ptr(pts), pts.shape[0], pts.shape[1] * 4, 0,
                                                              16 if pts.shape[1] >= 5 else -1, C.byref(opts), _ptr(pose)))
         return True
 

@@ -92,7 +92,7 @@ def organize(points: np.ndarray, intr, width: int, height: int, *, rgba_off: int
     intr = np.asarray(intr, np.float32)
     out = np.zeros((height, width, 8), np.float32)
     tf = None if world_to_camera is None else np.ascontiguousarray(world_to_camera, dtype=np.float64)
-    filled = lib.orc_organize(_ptr(pts), pts.shape[0], pts.strides[0], 0, rgba_off, _ptr(intr), width, height,
+    filled = lib.orc_organize(_ptr(pts), pts.shape[0], pts.shape[1] * 4, 0, rgba_off, _ptr(intr), width, height,
                               float(cloud_units), int(zero_nans), _ptr(tf), _ptr(out))
     return out, int(filled)
 

@@ -162,7 +162,7 @@ def organize(points, intr, width, height, *, rgba_off=-1, cloud_units=1.0, zero_
     intr = np.asarray(intr, np.float32)
     out = np.full((height, width, out_stride // 4), 7.0, np.float32)       # pre-filled: padding must come back zero
     tf = None if world_to_camera is None else np.ascontiguousarray(world_to_camera, dtype=np.float64)
-    filled = lib.emu_organize(_ptr(pts), pts.shape[0], pts.strides[0], 0, rgba_off, _ptr(intr), width, height,
+    filled = lib.emu_organize(_ptr(pts), pts.shape[0], pts.shape[1] * 4, 0, rgba_off, _ptr(intr), width, height,
                               float(cloud_units), int(zero_nans), _ptr(tf), _ptr(out), out_stride, out_rgba_off)
     return out, int(filled)
 
