@@ -89,14 +89,20 @@ void usage (const char* argv0)
                "  --device arg           CUDA device ordinal (default 0)\n  --pool-log2 arg        log2 of the brick pool capacity (default: library default)\n");
 }
 
-// integrate.cpp:224-246
+// integrate.cpp:224-246 (getSharedPrefix): the common prefix of the first and last (sorted) names, cut at the first
+// digit.  Deviation: the reference scans the whole path string, so a digit in a DIRECTORY name ("/data/run2/...")
+// cuts the prefix there and no pose file is ever matched; here the scan starts at the file name.
 std::string shared_prefix (const std::vector<std::string>& files)
 {
   const std::string& first = files.front ();
   const std::string& last = files.back ();
-  size_t i;
-  for (i = 0; i < first.length (); i++)
-    if (i >= last.length () || first[i] != last[i] || std::isdigit ((unsigned char) first[i])) break;
+  size_t i = fs::path (first).parent_path ().string ().length ();
+  if (first.compare (0, i, last, 0, i) != 0) i = 0;
+  for (; i < first.length (); i++)
+  {
+    bool in_name = i > fs::path (first).parent_path ().string ().length ();
+    if (i >= last.length () || first[i] != last[i] || (in_name && std::isdigit ((unsigned char) first[i]))) break;
+  }
   return first.substr (0, i);
 }
 

@@ -144,6 +144,22 @@ def test_integrate_program_argument_handling(progs, tmp_path):
     assert subprocess.run([progs["b200_tsdf2mesh"]], capture_output=True).returncode == 1
 
 
+def test_cloud_and_pose_files_are_paired_even_below_directories_with_digits(progs, tmp_path):
+    d = tmp_path / "run2" / "seq3"; d.mkdir(parents=True)
+    for f in range(3):
+        write_pcd(str(d / f"frame_{f:04d}.pcd"), sample_points(50), "binary")
+        (d / f"frame_{f:04d}.txt").write_text("1 0 0 0\n0 1 0 0\n0 0 1 0\n")
+    r = subprocess.run([progs["b200_integrate"], "--in", str(d), "--out", str(tmp_path / "o")], capture_output=True, text=True)
+    assert f"Found PCD files with prefix: {d}/frame_, poses with prefix: {d}/frame_" in r.stdout
+    assert "Could not find matching transform file" not in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode == 3 and "no CUDA device" in r.stderr                  # the product has no CPU path
+    (d / "frame_0001.txt").unlink()
+    r = subprocess.run([progs["b200_integrate"], "--in", str(d), "--out", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Could not find matching transform file" in r.stderr
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def read_ply(path):
     raw = open(path, "rb").read()

@@ -11,7 +11,8 @@ for r in rows:
     if r and r[0] == "Line No": hdr = r; continue
     if hdr and r and r[0] not in ("", "Function Name") and r[0].isdigit():
         d = dict(zip(hdr, r))
-        recs.append((cur_file, int(r[0]), r[1].strip(), int(d["Instructions Executed"] or 0), int(d["# Samples"] or 0)))
+        num = lambda v: int(v) if v and v.strip().lstrip("-").isdigit() else 0      # "-" = no data for the line
+        recs.append((cur_file, int(r[0]), r[1].strip(), num(d["Instructions Executed"]), num(d["# Samples"])))
 ti = sum(x[3] for x in recs); ts = sum(x[4] for x in recs)
 print(f"total warp instructions {ti}, stall samples {ts}")
 print("--- by instructions")
