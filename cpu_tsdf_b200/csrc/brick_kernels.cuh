@@ -295,6 +295,74 @@ __device__ __noinline__ int leaf_visit_warp8 (const Params& p, const Frame& f, c
   return __shfl_sync (0xffffffffu, rc, 0);
 }
 
+// The same leaf visit for up to FOUR nodes at once: the warp is split into four groups of eight lanes, group g
+// (lanes 8g..8g+7) visits node `n` (identical in the eight lanes of a group) when `active`; lane 8g+c handles child c
+// of a re-split.  All 32 lanes must call it.  Returns the group's node's return code in each of its lanes.
+// (A pruned-then-resplit node costs five or six dependent memory round trips; a cell that has many of them in one
+// frame used to serialise them and made its warp the straggler of k_celltop_up.)
+__device__ __noinline__ int leaf_visit_groups (const Params& p, const Frame& f, const NodePos& n, bool active,
+                                               unsigned long long& upd, unsigned long long& vis)
+{
+  const int lane = threadIdx.x & 31, sub = lane & 7, g = lane >> 3;
+  const unsigned gmask = 0xFFu << (8 * g);
+  Obs o; o.valid = false; o.near_ = false; o.u = o.v = 0; o.d_new = 0.f;
+  if (active) o = observe (p, f, n.cx, n.cy, n.cz, n.size);
+  const bool live = active && o.valid;                                  // !valid: return 0 without touching the node
+  const bool want_split = live && o.near_ && n.size > p.finest_size;
+  uint32_t m = 0; uint32_t* sw = nullptr;
+  int cs = -1;
+  if (want_split) { sw = split_word (p, n, m); if (sub == 0) cs = children_slot (p, n, true); }
+  cs = __shfl_sync (0xffffffffu, cs, 8 * g);
+  const bool split = want_split && cs >= 0;
+  if (split && sub == 0) atomicOr (sw, m);
+  __syncwarp ();
+  Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
+  int crc = -1;
+  NodePos ch = n;
+  if (split)
+  {
+    ch = make_child (p, n, sub, cs);
+    Obs oc = observe (p, f, ch.cx, ch.cy, ch.cz, ch.size);
+    crc = visit_fresh_leaf (p, f, ch, oc, cnt);
+  }
+  const unsigned nonneg = __ballot_sync (0xffffffffu, split && crc >= 0) & gmask;
+  upd += cnt.n_updates; vis += cnt.n_visits;
+  if (split && !nonneg)                                                 // children.clear () again
+  {
+    if (sub == 0) atomicAnd (sw, ~m);
+    reset_node (p, ch);
+  }
+  __syncwarp ();
+  int rc = 0;
+  if (split && nonneg) rc = 1;
+  else if (live && sub == 0) { bool updated; rc = leaf_update (p, f, n, o, updated); upd += updated; }
+  return __shfl_sync (0xffffffffu, rc, 8 * g);
+}
+// drives leaf_visit_groups over the lanes flagged in `slow` (each holding its node in `n`), four per round; a flagged
+// lane gets its node's return code in `rc`
+__device__ __forceinline__ void leaf_visit_slow_lanes (const Params& p, const Frame& f, bool slow, const NodePos& n, int t1, int& rc,
+                                                       unsigned long long& upd, unsigned long long& vis)
+{
+  const int lane = threadIdx.x & 31, g = lane >> 3;
+  uint32_t sm = __ballot_sync (0xffffffffu, slow);
+  while (sm)
+  {
+    int srcs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { srcs[k] = sm ? __ffs (sm) - 1 : -1; if (sm) sm &= sm - 1; }
+    int src = srcs[0]; if (g == 1) src = srcs[1]; if (g == 2) src = srcs[2]; if (g == 3) src = srcs[3];
+    const int from = src >= 0 ? src : 0;
+    NodePos q;
+    q.level = __shfl_sync (0xffffffffu, n.level, from); q.x = __shfl_sync (0xffffffffu, n.x, from); q.y = __shfl_sync (0xffffffffu, n.y, from); q.z = __shfl_sync (0xffffffffu, n.z, from);
+    q.cx = __shfl_sync (0xffffffffu, n.cx, from); q.cy = __shfl_sync (0xffffffffu, n.cy, from); q.cz = __shfl_sync (0xffffffffu, n.cz, from);
+    q.size = __shfl_sync (0xffffffffu, n.size, from); q.slot = t1; q.idx = __shfl_sync (0xffffffffu, n.idx, from);
+    __threadfence_block ();
+    const int r = leaf_visit_groups (p, f, q, src >= 0, upd, vis);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int rk = __shfl_sync (0xffffffffu, r, 8 * k); if (lane == srcs[k]) rc = rk; }
+  }
+}
+
 constexpr int RC_DEFERRED = 2;   // upper_fold: the node needs the general leaf visit (caller decides how)
 __device__ __forceinline__ int upper_fold (const Params& p, const Frame& f, int level, const QNode& e, bool all_empty,
                                            unsigned long long& upd, unsigned long long& vis, bool defer_slow = false)
@@ -1123,19 +1191,8 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
           else slow = true;
         }
       }
-      // pre-existing children pruned: leaf visit by the whole warp, one node at a time (rare)
-      uint32_t sm = __ballot_sync (0xffffffffu, slow);
-      while (sm)
-      {
-        const int src = __ffs (sm) - 1; sm &= sm - 1;
-        NodePos q;
-        q.level = __shfl_sync (0xffffffffu, n.level, src); q.x = __shfl_sync (0xffffffffu, n.x, src); q.y = __shfl_sync (0xffffffffu, n.y, src); q.z = __shfl_sync (0xffffffffu, n.z, src);
-        q.cx = __shfl_sync (0xffffffffu, n.cx, src); q.cy = __shfl_sync (0xffffffffu, n.cy, src); q.cz = __shfl_sync (0xffffffffu, n.cz, src);
-        q.size = __shfl_sync (0xffffffffu, n.size, src); q.slot = t1; q.idx = __shfl_sync (0xffffffffu, n.idx, src);
-        __threadfence_block ();
-        int r = leaf_visit_warp8 (p, f, q, upd, vis);
-        if (lane == src) rc = r;
-      }
+      // pre-existing children pruned: leaf visits, four nodes per round (eight lanes each)
+      leaf_visit_slow_lanes (p, f, slow, n, t1, rc, upd, vis);
       const bool visited2 = (int1 >> (j2 >> 3)) & 1;
       nonneg2[i2] = __ballot_sync (0xffffffffu, visited2 && rc >= 0);
     }
@@ -1159,18 +1216,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
           else slow = true;
         }
       }
-      uint32_t sm = __ballot_sync (0xffffffffu, slow);
-      while (sm)
-      {
-        const int src = __ffs (sm) - 1; sm &= sm - 1;
-        NodePos q;
-        q.level = __shfl_sync (0xffffffffu, n.level, src); q.x = __shfl_sync (0xffffffffu, n.x, src); q.y = __shfl_sync (0xffffffffu, n.y, src); q.z = __shfl_sync (0xffffffffu, n.z, src);
-        q.cx = __shfl_sync (0xffffffffu, n.cx, src); q.cy = __shfl_sync (0xffffffffu, n.cy, src); q.cz = __shfl_sync (0xffffffffu, n.cz, src);
-        q.size = __shfl_sync (0xffffffffu, n.size, src); q.slot = t1; q.idx = __shfl_sync (0xffffffffu, n.idx, src);
-        __threadfence_block ();
-        int r = leaf_visit_warp8 (p, f, q, upd, vis);
-        if (lane == src) rc1 = r;
-      }
+      leaf_visit_slow_lanes (p, f, slow, n, t1, rc1, upd, vis);
     }
     const uint32_t nonneg1 = __ballot_sync (0xffffffffu, lane < 8 && rc1 >= 0);
     // ---- the cell ----

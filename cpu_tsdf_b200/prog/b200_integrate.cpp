@@ -46,7 +46,7 @@ const char* const kValueOpts[] = { "in", "out", "volume-size", "cell-size", "max
   "num-random-splits", "fx", "fy", "cx", "cy", "cloud-units", "pose-units", "max-sensor-dist", "min-sensor-dist",
   "trunc-dist-pos", "trunc-dist-neg", "min-weight", "device", "pool-log2" };
 const char* const kFlagOpts[] = { "help", "save-tsdf", "visualize", "verbose", "color", "flatten", "cleanup", "invert", "world",
-  "organized", "zero-nans", "save-ascii", "cloud-only" };
+  "organized", "zero-nans", "save-ascii", "cloud-only", "exact-vol" };
 
 bool parse (int argc, char** argv, Options& o, std::string& err)
 {
@@ -86,6 +86,8 @@ void usage (const char* argv0)
                "  --pose-units arg       Units of the poses, in meters\n  --max-sensor-dist arg  Maximum distance data can be from the sensor (3.0)\n"
                "  --min-sensor-dist arg  Minimum distance data can be from the sensor (0)\n  --trunc-dist-pos arg   Positive truncation distance (0.03)\n"
                "  --trunc-dist-neg arg   Negative truncation distance (0.03)\n  --min-weight arg       Minimum weight to render (0)\n"
+               "  --exact-vol            Keep the per-voxel variance accumulators so that volume.tsdf is byte-identical to the\n"
+               "                         reference's (slower: selects the general update kernel)\n"
                "  --device arg           CUDA device ordinal (default 0)\n  --pool-log2 arg        log2 of the brick pool capacity (default: library default)\n");
 }
 
@@ -194,6 +196,7 @@ int main (int argc, char** argv)
   tsdf->setSensorDistanceBounds (min_sensor_dist, max_sensor_dist);
   tsdf->setIntegrateColor (integrate_color);
   tsdf->setDepthTruncationLimits (trunc_dist_pos, trunc_dist_neg);
+  tsdf->setTrackVariance (opts.has ("exact-vol"));
   tsdf->reset ();
   if (!tsdf->ok ()) { std::fprintf (stderr, "reset failed: %s\n", tsdf->lastError ()); return 3; }
   // :527-676

@@ -122,6 +122,9 @@ public:
   void getCameraIntrinsics (double& fx, double& fy, double& cx, double& cy) const { fx = cfg_.fx; fy = cfg_.fy; cx = cfg_.cx; cy = cfg_.cy; }
   void setMaxVoxelSize (float x, float y, float z) { cfg_.max_cell_x = x; cfg_.max_cell_y = y; cfg_.max_cell_z = z; push (); }
   void setIntegrateColor (bool integrate_color) { cfg_.integrate_color = integrate_color; push (); }
+  // B200 extension: keep OctreeNode::M_ / nsample_ (octree.cpp:160-161) so that save() writes them as the reference does
+  // (they are unused by every default code path; tracking them selects the general, slower update kernel)
+  void setTrackVariance (bool track) { cfg_.track_variance = track ? 1 : 0; push (); }
 
   // ---- the volumetric path ----
   void reset () { status_ = h_ ? b200tsdf_reset (h_) : B200TSDF_ENODEVICE; }                      // cpp:201-219

@@ -206,15 +206,19 @@ def test_integrate_program_end_to_end_matches_the_oracle_pipeline(progs, tmp_pat
         # so pose_rel_to_first_frame is the pose itself)
         org, _ = oracle_py.organize(cloud, intr, CAM.width, CAM.height, rgba_off=16, cloud_units=0.001, zero_nans=True)
         o.integrate(org, pose)
-    r = subprocess.run([progs["b200_integrate"], "--in", str(d), "--out", str(out), "--volume-size", "3", "--cell-size", "0.0117",
-                        "--color", "--cloud-units", "0.001", "--zero-nans", "--save-tsdf", "--flatten", "--cleanup", "--pool-log2", "16"],
-                       capture_output=True, text=True)
+    args = [progs["b200_integrate"], "--in", str(d), "--volume-size", "3", "--cell-size", "0.0117", "--color", "--cloud-units", "0.001",
+            "--zero-nans", "--save-tsdf", "--flatten", "--cleanup", "--pool-log2", "16"]
+    r = subprocess.run(args + ["--out", str(out)], capture_output=True, text=True)                   # the fast update kernels
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "Setting resolution: 256" in r.stdout
-    # the volume on disk is byte-identical to the oracle's
+    # with the variance accumulators kept (general update kernel) the volume on disk is byte-identical to the oracle's
+    out2 = tmp_path / "out_exact"
+    r = subprocess.run(args + ["--out", str(out2), "--exact-vol"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     ref_vol = str(tmp_path / "ref.vol")
     assert o.save(ref_vol) == 0
-    assert open(ref_vol, "rb").read() == open(out / "volume.tsdf", "rb").read()
+    assert open(ref_vol, "rb").read() == open(out2 / "volume.tsdf", "rb").read()
+    assert open(out / "mesh.ply", "rb").read() == open(out2 / "mesh.ply", "rb").read()
     # the mesh: marching cubes (min weight 0, coloured), flattenVertices, cleanupMesh
     verts, _ = o.mesh(0.0, 1)
     soup = (np.asarray(verts, np.float32).reshape(-1, 3), np.arange(len(verts), dtype=np.int32).reshape(-1, 3))
@@ -224,7 +228,7 @@ def test_integrate_program_end_to_end_matches_the_oracle_pipeline(progs, tmp_pat
     assert np.array_equal(want[0].view(np.uint32), gv.view(np.uint32)) and np.array_equal(want[1], gt)
     # tsdf2mesh on the saved volume: the plain soup, binary PLY
     ply2 = str(tmp_path / "m2.ply")
-    assert subprocess.run([progs["b200_tsdf2mesh"], str(out / "volume.tsdf"), ply2], capture_output=True).returncode == 0
+    assert subprocess.run([progs["b200_tsdf2mesh"], str(out2 / "volume.tsdf"), ply2], capture_output=True).returncode == 0
     v2, c2, t2 = read_ply(ply2)
     w2, _ = o.mesh(2.5, 0)                                                          # MarchingCubesTSDFOctree's default min weight
     assert c2 is None and np.array_equal(np.asarray(w2, np.float32).reshape(-1, 3).view(np.uint32), v2.view(np.uint32))
