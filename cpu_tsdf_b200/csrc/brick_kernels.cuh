@@ -247,6 +247,7 @@ __device__ __forceinline__ int upper_visit (const Params& p, const Frame& f, int
 
 // fold the children's return codes into an interior node (hpp:131-142 / :176-188 + fall-through)
 __device__ unsigned long long* g_diag;   // [0] slow folds in the upper sweeps, [1] visits inside them (diagnostics)
+__device__ unsigned long long* g_dbg;    // optional phase timing of k_celltop_up (b200tsdf_debug_timing), normally null
 __device__ __noinline__ int upper_fold_slow (const Params& p, const Frame& f, const NodePos& n, unsigned long long& upd, unsigned long long& vis)
 {
   Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
@@ -1118,8 +1119,11 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
   const float sizeC = level_size (p, p.C);
   const float off1 = sizeC * 0.25f;
   constexpr int STRIDE = 585;
+  const long long c_entry = clock64 ();
   for (int ci = warp; ci < count; ci += nwarps)
   {
+    const long long tc0 = clock64 ();
+    int dbg_slow2 = 0, dbg_slow1 = 0, dbg_ft = 0;
     const CellTop* top = tops + ci;
     const int t1 = top->t1slot;
     if (t1 < 0) continue;                                            // the cell was a leaf: nothing to fold
@@ -1165,6 +1169,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
         if (lane == i) nonneg_mine = nn;
       }
     }
+    const long long cA = clock64 ();
     // ---- level 2 ----
     uint32_t nonneg2[2];
 #pragma unroll
@@ -1187,15 +1192,17 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
           n.level = p.C + 2; n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.25f; n.slot = t1; n.idx = 8 + j2;
           { int lx = 0, ly = 0, lz = 0; for (int q = 1; q >= 0; --q) { int cc = (j2 >> (3 * q)) & 7; lx = (lx << 1) | (cc >> 2); ly = (ly << 1) | ((cc >> 1) & 1); lz = (lz << 1) | (cc & 1); }
             n.x = (cell.x << 2) | lx; n.y = (cell.y << 2) | ly; n.z = (cell.z << 2) | lz; }
-          if (kind2[i2] == KIND_NEW) rc = top_fallthrough_new (p, f, n, top->dnew[9 + j2], top->uv[9 + j2], upd);
+          if (kind2[i2] == KIND_NEW) { rc = top_fallthrough_new (p, f, n, top->dnew[9 + j2], top->uv[9 + j2], upd); dbg_ft++; }
           else slow = true;
         }
       }
       // pre-existing children pruned: leaf visits, four nodes per round (eight lanes each)
+      dbg_slow2 += __popc (__ballot_sync (0xffffffffu, slow));
       leaf_visit_slow_lanes (p, f, slow, n, t1, rc, upd, vis);
       const bool visited2 = (int1 >> (j2 >> 3)) & 1;
       nonneg2[i2] = __ballot_sync (0xffffffffu, visited2 && rc >= 0);
     }
+    const long long cB = clock64 ();
     // ---- level 1 ----
     int rc1 = lane < 8 ? (int) top->rc[1 + lane] : 0;
     {
@@ -1216,18 +1223,36 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
           else slow = true;
         }
       }
+      dbg_slow1 += __popc (__ballot_sync (0xffffffffu, slow));
       leaf_visit_slow_lanes (p, f, slow, n, t1, rc1, upd, vis);
     }
     const uint32_t nonneg1 = __ballot_sync (0xffffffffu, lane < 8 && rc1 >= 0);
+    const long long cC = clock64 ();
+    int dbg_cell = 0;
     // ---- the cell ----
     if ((nonneg1 & 0xFFu) == 0)
     {
+      dbg_cell = top->kind[0] == KIND_NEW ? 1 : 2;
       NodePos nc; nc.level = p.C; nc.x = cell.x; nc.y = cell.y; nc.z = cell.z; nc.cx = c0[0]; nc.cy = c0[1]; nc.cz = c0[2]; nc.size = sizeC; nc.slot = -1; nc.idx = cell.idx;
       if (lane == 0) { uint32_t m; uint32_t* sw = split_word (p, nc, m); atomicAnd (sw, ~m); }
       if (lane < 8) { gdw[lane] = make_float2 (-1.f, 0.f); if (COLOR) grgb[lane] = make_uchar4 (0, 0, 0, 0); }
       __syncwarp ();
       if (top->kind[0] == KIND_NEW) { if (lane == 0) top_fallthrough_new (p, f, nc, top->dnew[0], top->uv[0], upd); }
       else { __threadfence_block (); leaf_visit_warp8 (p, f, nc, upd, vis); }
+    }
+    if (g_dbg && lane == 0)
+    {
+      const long long cD = clock64 ();
+      const unsigned long long tag = ((unsigned long long) (dbg_slow2 & 0xFF) << 24) | ((unsigned long long) (dbg_slow1 & 0xF) << 20) | ((unsigned long long) (dbg_cell & 3) << 18) | (unsigned long long) (ci & 0x3FFFF);
+      atomicMax (&g_dbg[0], ((unsigned long long) (cD - tc0) << 32) | tag);
+      atomicMax (&g_dbg[1], ((unsigned long long) (cA - tc0) << 32) | tag);
+      atomicMax (&g_dbg[2], ((unsigned long long) (cB - cA) << 32) | tag);
+      atomicMax (&g_dbg[3], ((unsigned long long) (cC - cB) << 32) | tag);
+      atomicMax (&g_dbg[4], ((unsigned long long) (cD - cC) << 32) | tag);
+      atomicMax (&g_dbg[5], ((unsigned long long) (tc0 - c_entry) << 32) | tag);
+      atomicAdd (&g_dbg[6], (unsigned long long) dbg_slow2); atomicAdd (&g_dbg[7], (unsigned long long) dbg_slow1);
+      atomicAdd (&g_dbg[8], (unsigned long long) (dbg_cell == 2)); atomicAdd (&g_dbg[9], (unsigned long long) (dbg_cell == 1));
+      atomicAdd (&g_dbg[10], 1ull);
     }
   }
   __syncwarp ();

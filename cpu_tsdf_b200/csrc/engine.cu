@@ -9,6 +9,7 @@
 #include "params_setup.h"
 #include "brick_kernels.cuh"
 #include "organize.cuh"
+#include "mesh_sort.h"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -287,7 +288,8 @@ __device__ __forceinline__ bool brick_root_is_split (const Params& p, int t, int
 
 template <bool EMIT>
 __global__ void k_mesh_bricks (Params gp, McParams mc, const int* __restrict__ list, int nbricks,
-                               unsigned long long* __restrict__ total, float* __restrict__ verts, unsigned char* __restrict__ cols)
+                               unsigned long long* __restrict__ total, float* __restrict__ verts, unsigned char* __restrict__ cols,
+                               unsigned long long* __restrict__ okeys)
 {
   B2_STAGE_PARAMS (gp)
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -339,13 +341,16 @@ __global__ void k_mesh_bricks (Params gp, McParams mc, const int* __restrict__ l
       size_t tri0 = (size_t) wbase + (incl - ntri);
       mc_leaf (p, mc, n, dw.x, dw.y, b200tsdf_mc::edge_table, b200tsdf_mc::tri_table,
                verts + tri0 * 9, cols ? cols + tri0 * 9 : nullptr);
+      const unsigned long long k = mc_order_key (p, n) << 3;
+      for (int t = 0; t < ntri; ++t) okeys[tri0 + t] = k | (unsigned long long) t;
     }
   }
 }
 
 // leaves held in the root arrays (unsplit coarse cells when Rtop == C)
 template <bool EMIT>
-__global__ void k_mesh_roots (Params gp, McParams mc, unsigned long long* __restrict__ total, float* __restrict__ verts, unsigned char* __restrict__ cols)
+__global__ void k_mesh_roots (Params gp, McParams mc, unsigned long long* __restrict__ total, float* __restrict__ verts, unsigned char* __restrict__ cols,
+                              unsigned long long* __restrict__ okeys)
 {
   B2_STAGE_PARAMS (gp)
   int n = 1 << p.Rtop;
@@ -358,7 +363,12 @@ __global__ void k_mesh_roots (Params gp, McParams mc, unsigned long long* __rest
   int ntri = mc_leaf (p, mc, nd, dw.x, dw.y, b200tsdf_mc::edge_table, b200tsdf_mc::tri_table, nullptr, nullptr);
   if (!ntri) return;
   unsigned long long base = atomicAdd (total, (unsigned long long) ntri);
-  if (EMIT) mc_leaf (p, mc, nd, dw.x, dw.y, b200tsdf_mc::edge_table, b200tsdf_mc::tri_table, verts + base * 9, cols ? cols + base * 9 : nullptr);
+  if (EMIT)
+  {
+    mc_leaf (p, mc, nd, dw.x, dw.y, b200tsdf_mc::edge_table, b200tsdf_mc::tri_table, verts + base * 9, cols ? cols + base * 9 : nullptr);
+    const unsigned long long k = mc_order_key (p, nd) << 3;
+    for (int t = 0; t < ntri; ++t) okeys[base + t] = k | (unsigned long long) t;
+  }
 }
 
 } // namespace
@@ -1001,8 +1011,8 @@ int b200tsdf_mesh (b200tsdf_t* h, float w_min, int color_mode, float** verts, ui
   CK (cudaMemcpyAsync (&nb, d_n, sizeof (int), cudaMemcpyDeviceToHost, s));
   CK (cudaStreamSynchronize (s));
   int root_n = (int) h->root_n;
-  if (nb) k_mesh_bricks<false><<<(nb * 32 + 127) / 128, 128, 0, s>>> (p, mc, d_list, nb, d_total, nullptr, nullptr);
-  k_mesh_roots<false><<<(root_n + 127) / 128, 128, 0, s>>> (p, mc, d_total, nullptr, nullptr);
+  if (nb) k_mesh_bricks<false><<<(nb * 32 + 127) / 128, 128, 0, s>>> (p, mc, d_list, nb, d_total, nullptr, nullptr, nullptr);
+  k_mesh_roots<false><<<(root_n + 127) / 128, 128, 0, s>>> (p, mc, d_total, nullptr, nullptr, nullptr);
   unsigned long long ntri = 0;
   CK (cudaMemcpyAsync (&ntri, d_total, sizeof (ntri), cudaMemcpyDeviceToHost, s));
   CK (cudaStreamSynchronize (s));
@@ -1010,17 +1020,22 @@ int b200tsdf_mesh (b200tsdf_t* h, float w_min, int color_mode, float** verts, ui
   *verts = nullptr; if (rgb) *rgb = nullptr; *nverts = (size_t) ntri * 3;
   if (ntri)
   {
-    float* d_v = nullptr; unsigned char* d_c = nullptr;
-    CK (cudaMalloc (&d_v, ntri * 9 * sizeof (float)));
-    if (color_mode) CK (cudaMalloc (&d_c, ntri * 9));
+    // emission order depends on the hash layout and on atomics; the triangles are then sorted into the reference's
+    // own order (depth first over the octree, mc_order_key) so that the soup is reproducible and comparable as is
+    float *d_v = nullptr, *d_v2 = nullptr; unsigned char *d_c = nullptr, *d_c2 = nullptr; unsigned long long* d_k = nullptr;
+    CK (cudaMalloc (&d_v, ntri * 9 * sizeof (float))); CK (cudaMalloc (&d_v2, ntri * 9 * sizeof (float)));
+    CK (cudaMalloc (&d_k, ntri * sizeof (unsigned long long)));
+    if (color_mode) { CK (cudaMalloc (&d_c, ntri * 9)); CK (cudaMalloc (&d_c2, ntri * 9)); }
     CK (cudaMemsetAsync (d_total, 0, sizeof (unsigned long long), s));
-    if (nb) k_mesh_bricks<true><<<(nb * 32 + 127) / 128, 128, 0, s>>> (p, mc, d_list, nb, d_total, d_v, d_c);
-    k_mesh_roots<true><<<(root_n + 127) / 128, 128, 0, s>>> (p, mc, d_total, d_v, d_c);
+    if (nb) k_mesh_bricks<true><<<(nb * 32 + 127) / 128, 128, 0, s>>> (p, mc, d_list, nb, d_total, d_v, d_c, d_k);
+    k_mesh_roots<true><<<(root_n + 127) / 128, 128, 0, s>>> (p, mc, d_total, d_v, d_c, d_k);
+    if (b2_sort_triangles (s, (size_t) ntri, 3 * p.L + 3, d_k, d_v, d_c, d_v2, d_c2) != 0)
+    { cudaFree (d_v); cudaFree (d_v2); cudaFree (d_c); cudaFree (d_c2); cudaFree (d_k); cudaFree (d_list); return h->fail (B200TSDF_ECUDA, "triangle sort failed"); }
     h->mesh_v = (float*) std::malloc (ntri * 9 * sizeof (float));
-    CK (cudaMemcpyAsync (h->mesh_v, d_v, ntri * 9 * sizeof (float), cudaMemcpyDeviceToHost, s));
-    if (color_mode) { h->mesh_c = (unsigned char*) std::malloc (ntri * 9); CK (cudaMemcpyAsync (h->mesh_c, d_c, ntri * 9, cudaMemcpyDeviceToHost, s)); }
+    CK (cudaMemcpyAsync (h->mesh_v, d_v2, ntri * 9 * sizeof (float), cudaMemcpyDeviceToHost, s));
+    if (color_mode) { h->mesh_c = (unsigned char*) std::malloc (ntri * 9); CK (cudaMemcpyAsync (h->mesh_c, d_c2, ntri * 9, cudaMemcpyDeviceToHost, s)); }
     CK (cudaStreamSynchronize (s));
-    cudaFree (d_v); cudaFree (d_c);
+    cudaFree (d_v); cudaFree (d_v2); cudaFree (d_c); cudaFree (d_c2); cudaFree (d_k);
     *verts = h->mesh_v; if (rgb) *rgb = h->mesh_c;
   }
   cudaFree (d_list);
@@ -1068,6 +1083,25 @@ int b200tsdf_frustum_cull (b200tsdf_t* h, const double* pose, uint8_t* mask, int
 } // extern "C"
 
 extern "C" {
+
+// Diagnostics (not part of include/b200tsdf.h): phase timing of k_celltop_up.  First call arms it; every call returns and
+// clears the 16 counters ([0..5] max SM cycles << 32 | tag of total / level-3 / level-2 / level-1 / cell / wait-before-first-cell,
+// [6..10] slow level-2 nodes, slow level-1 nodes, cell leaf visits, cell fall-throughs, cells folded).
+int b200tsdf_debug_timing (b200tsdf_t* h, unsigned long long* out16)
+{
+  static unsigned long long* d_dbg = nullptr;
+  if (!h || !out16) return B200TSDF_EINVAL;
+  cudaSetDevice (h->device);
+  CK (cudaStreamSynchronize (h->stream));
+  if (!d_dbg)
+  {
+    CK (cudaMalloc (&d_dbg, 16 * 8)); CK (cudaMemset (d_dbg, 0, 16 * 8));
+    CK (cudaMemcpyToSymbol (g_dbg, &d_dbg, sizeof (d_dbg)));
+  }
+  CK (cudaMemcpy (out16, d_dbg, 16 * 8, cudaMemcpyDeviceToHost));
+  CK (cudaMemset (d_dbg, 0, 16 * 8));
+  return B200TSDF_OK;
+}
 
 int b200tsdf_profile_begin (b200tsdf_t* h)
 {

@@ -4,6 +4,9 @@
 #include "../../include/b200tsdf.h"
 #include "meshpost_core.cuh"
 
+#include "mesh_sort.h"
+
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 #include <cstdlib>
@@ -340,4 +343,38 @@ extern "C" int b200tsdf_mesh_cleanup (int device, const float* verts, size_t nve
   }
   MCK (cudaGetLastError ());
   return download_mesh (B, d_verts_out, nv_new, d_tris_out, nt_new, out_verts, out_nverts, out_tris, out_ntris);
+}
+
+// ---- triangle ordering for b200tsdf_mesh (engine.cu) -----------------------------------------------------------------
+namespace {
+__global__ void k_gather_triangles (const unsigned int* __restrict__ order, size_t ntri, const float* __restrict__ v, const unsigned char* __restrict__ c,
+                                    float* __restrict__ vo, unsigned char* __restrict__ co)
+{
+  // nine threads per triangle: thread q copies float q (and colour byte q) of the triangle
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntri * 9) return;
+  size_t t = i / 9, q = i - t * 9, src = (size_t) order[t] * 9 + q;
+  vo[i] = v[src];
+  if (c) co[i] = c[src];
+}
+}
+
+int b2_sort_triangles (cudaStream_t s, size_t ntri, int key_bits, unsigned long long* d_keys, const float* d_v, const unsigned char* d_c,
+                       float* d_v_out, unsigned char* d_c_out)
+{
+  if (!ntri) return 0;
+  if (ntri >= ((size_t) 1 << 31)) return (int) cudaErrorInvalidValue;
+  unsigned long long* keys2 = nullptr; unsigned int *idx = nullptr, *idx2 = nullptr; void* tmp = nullptr;
+  size_t bytes = 0;
+  cudaError_t e = cudaMalloc (&keys2, ntri * 8);
+  if (e == cudaSuccess) e = cudaMalloc (&idx, ntri * 4);
+  if (e == cudaSuccess) e = cudaMalloc (&idx2, ntri * 4);
+  if (e == cudaSuccess) { k_iota<<<nblk (ntri), TPB, 0, s>>> ((int*) idx, (int) ntri); e = cudaGetLastError (); }
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs (nullptr, bytes, d_keys, keys2, idx, idx2, (int) ntri, 0, key_bits, s);
+  if (e == cudaSuccess) e = cudaMalloc (&tmp, bytes);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs (tmp, bytes, d_keys, keys2, idx, idx2, (int) ntri, 0, key_bits, s);
+  if (e == cudaSuccess) { k_gather_triangles<<<nblk (ntri * 9), TPB, 0, s>>> (idx2, ntri, d_v, d_c, d_v_out, d_c_out); e = cudaGetLastError (); }
+  if (e == cudaSuccess) e = cudaStreamSynchronize (s);
+  cudaFree (keys2); cudaFree (idx); cudaFree (idx2); cudaFree (tmp);
+  return (int) e;
 }

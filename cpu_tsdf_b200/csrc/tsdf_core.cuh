@@ -972,6 +972,19 @@ struct McParams
   double gt[12];                // global transform rows 0..2
 };
 
+// Position of a leaf in the reference's mesh order.  performReconstruction walks the octree depth first with the
+// children in index order (octree.cpp:257-264: x is the high bit, then y, then z), one cube per leaf, so leaves come
+// out sorted by the bit-interleaved finest-level coordinates of their first voxel; a cube's triangles follow in
+// table order (key << 3 | triangle).
+B2_HD unsigned long long mc_order_key (const Params& p, const NodePos& n)
+{
+  const int sh = p.L - n.level;
+  const unsigned X = (unsigned) n.x << sh, Y = (unsigned) n.y << sh, Z = (unsigned) n.z << sh;
+  unsigned long long k = 0;
+  for (int l = p.L - 1; l >= 0; --l) k = (k << 3) | (((X >> l) & 1u) << 2) | (((Y >> l) & 1u) << 1) | ((Z >> l) & 1u);
+  return k;
+}
+
 // getGridValue (cpp:91-106)
 B2_HD float mc_grid_value (const Params& p, const McParams& mc, int x, int y, int z)
 {

@@ -205,7 +205,8 @@ long long emu_mesh (Emu* e, float w_min, int color_mode, const float** verts, co
   make_mc_params (e->cfg, p, w_min, color_mode, mc);
   std::vector<Rec> recs;
   e->mesh_v.clear (); e->mesh_c.clear ();
-  // every leaf, any level (order is irrelevant: tests compare sorted soups)
+  // every leaf, any level, visited in an arbitrary (stack) order and then sorted by the order key
+  std::vector<std::pair<unsigned long long, size_t> > order;
   int n = 1 << p.C;
   std::vector<NodePos> stack;
   for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z)
@@ -226,7 +227,20 @@ long long emu_mesh (Emu* e, float w_min, int color_mode, const float** verts, co
       float v[45]; unsigned char cc[45];
       int nt = mc_leaf (p, mc, q, dw.x, dw.y, mc_tables::edge_table, mc_tables::tri_table, v, color_mode ? cc : nullptr);
       for (int i = 0; i < 9 * nt; ++i) { e->mesh_v.push_back (v[i]); if (color_mode) e->mesh_c.push_back (cc[i]); }
+      for (int t = 0; t < nt; ++t) order.push_back ({ (mc_order_key (p, q) << 3) | (unsigned long long) t, order.size () });
     }
+  }
+  // the engine sorts its (unordered) emission by mc_order_key: the result must be the reference's own order
+  std::sort (order.begin (), order.end ());
+  {
+    std::vector<float> sv (e->mesh_v.size ()); std::vector<unsigned char> sc (e->mesh_c.size ());
+    for (size_t t = 0; t < order.size (); ++t)
+    {
+      size_t src = order[t].second;
+      std::copy (e->mesh_v.begin () + 9 * src, e->mesh_v.begin () + 9 * src + 9, sv.begin () + 9 * t);
+      if (color_mode) std::copy (e->mesh_c.begin () + 9 * src, e->mesh_c.begin () + 9 * src + 9, sc.begin () + 9 * t);
+    }
+    e->mesh_v.swap (sv); e->mesh_c.swap (sc);
   }
   *verts = e->mesh_v.data ();
   if (cols) *cols = color_mode ? e->mesh_c.data () : nullptr;

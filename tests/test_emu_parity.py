@@ -120,6 +120,9 @@ def test_queries_render_mesh_256():
         va, cola = o.mesh(wmin, cm); vb, colb = e.mesh(wmin, cm)
         assert len(va) == len(vb) > 3000
         assert np.array_equal(canon_soup(va, cola), canon_soup(vb, colb))
+        # and in the reference's own triangle order (depth-first over the octree): the engine sorts by mc_order_key
+        assert np.array_equal(np.asarray(va).view(np.uint32), np.asarray(vb).view(np.uint32))
+        assert cola is None or np.array_equal(cola, colb)
 
 
 def test_global_transform_applies_to_mesh_only():

@@ -97,6 +97,8 @@ def test_interior_2048_config3_color_mesh():
         va, ca = o.mesh(wmin, 1 if rgb else 0)
         assert len(va) == len(vb) > 10000 and len(polys) * 3 == len(vb)
         assert np.array_equal(canon_soup(va, ca), canon_soup(vb, cb))
+        # and triangle for triangle in the reference's own order (the engine sorts its emission by mc_order_key)
+        assert np.array_equal(np.asarray(va).view(np.uint32), np.asarray(vb).reshape(-1, 3).view(np.uint32)) and (ca is None or np.array_equal(ca, cb))
         assert np.abs(canon_soup(va)[:, :9] - canon_soup(vb)[:, :9]).max() <= 1e-5   # north-star bar
 
 
@@ -180,6 +182,7 @@ def test_queries_render_mesh_256():
         va, cola = o.mesh(wmin, cm)
         assert len(va) == len(vb) > 3000
         assert np.array_equal(canon_soup(va, cola), canon_soup(vb, colb))
+        assert np.array_equal(np.asarray(va).view(np.uint32), np.asarray(vb).reshape(-1, 3).view(np.uint32)) and (cola is None or np.array_equal(cola, colb))
 
 
 def test_save_vol_matches_oracle_bytes(tmp_path):
