@@ -296,6 +296,47 @@ __device__ __noinline__ int leaf_visit_warp8 (const Params& p, const Frame& f, c
   return __shfl_sync (0xffffffffu, rc, 0);
 }
 
+// The leaf visit of a COARSE node by the whole warp with the breadth-first routine (tsdf_core.cuh, fresh_children_bfs):
+// a re-split coarse cell drags a subtree of a few dozen fresh nodes over three or four levels behind it, which the
+// eight-lane version above walks depth first, one lane per child (~40 us, the straggler of k_celltop_up).  rec/counter:
+// this warp's FRESH_RECS records and one int in shared memory.
+constexpr int FRESH_RECS = 128;
+struct CoopWarp
+{
+  __device__ __forceinline__ int lane () const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int nlanes () const { return 32; }
+  __device__ __forceinline__ void sync () const { __syncwarp (); }
+};
+__device__ __noinline__ int leaf_visit_warp_bfs (const Params& p, const Frame& f, const NodePos& n, FreshRec* rec, int* counter,
+                                                 unsigned long long& upd, unsigned long long& vis)
+{
+  const int lane = threadIdx.x & 31;
+  Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
+  if (!o.valid) return 0;
+  if (o.near_ && n.size > p.finest_size)
+  {
+    uint32_t m; uint32_t* sw = split_word (p, n, m);
+    int cs = -1;
+    if (lane == 0) cs = children_slot (p, n, true);
+    cs = __shfl_sync (0xffffffffu, cs, 0);
+    if (cs >= 0)
+    {
+      if (lane == 0) atomicOr (sw, m);
+      __syncwarp ();
+      Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
+      const bool stays = fresh_children_bfs (p, f, n, cs, rec, FRESH_RECS, counter, CoopWarp (), cnt);
+      upd += cnt.n_updates; vis += cnt.n_visits;
+      if (stays) return 1;
+      if (lane == 0) atomicAnd (sw, ~m);
+      if (lane < 8) reset_node (p, rec[lane].n);
+      __syncwarp ();
+    }
+  }
+  int rc = 0;
+  if (lane == 0) { bool updated; rc = leaf_update (p, f, n, o, updated); upd += updated; }
+  return __shfl_sync (0xffffffffu, rc, 0);
+}
+
 // The same leaf visit for up to FOUR nodes at once: the warp is split into four groups of eight lanes, group g
 // (lanes 8g..8g+7) visits node `n` (identical in the eight lanes of a group) when `active`; lane 8g+c handles child c
 // of a re-split.  All 32 lanes must call it.  Returns the group's node's return code in each of its lanes.
@@ -1102,6 +1143,8 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
   // would otherwise make every thread copy the kernel parameters to its stack in the prologue
   __shared__ Params sp_;
   __shared__ Frame sf_;
+  __shared__ FreshRec s_rec[4][FRESH_RECS];          // per-warp records of the breadth-first re-split visit
+  __shared__ int s_cnt[4];
   {
     const int* s1 = reinterpret_cast<const int*> (&gp); int* d1 = reinterpret_cast<int*> (&sp_);
     for (int w = threadIdx.x; w < (int) (sizeof (Params) / sizeof (int)); w += blockDim.x) d1[w] = s1[w];
@@ -1238,7 +1281,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
       if (lane < 8) { gdw[lane] = make_float2 (-1.f, 0.f); if (COLOR) grgb[lane] = make_uchar4 (0, 0, 0, 0); }
       __syncwarp ();
       if (top->kind[0] == KIND_NEW) { if (lane == 0) top_fallthrough_new (p, f, nc, top->dnew[0], top->uv[0], upd); }
-      else { __threadfence_block (); leaf_visit_warp8 (p, f, nc, upd, vis); }
+      else { __threadfence_block (); leaf_visit_warp_bfs (p, f, nc, s_rec[threadIdx.x >> 5], &s_cnt[threadIdx.x >> 5], upd, vis); }
     }
     if (g_dbg && lane == 0)
     {

@@ -552,16 +552,9 @@ struct Counters { long long n_updates, n_visits; };
 // keeps the (latency-bound) general path short.
 B2_HDN inline bool split_and_expand (const Params& p, const Frame& f, const NodePos& n, uint32_t* sw, uint32_t smask, Counters& cnt);
 
-B2_HDN inline int visit_fresh_leaf (const Params& p, const Frame& f, const NodePos& n, const Obs& o, Counters& cnt)
+// leaf update (hpp:189-214) of a node known to be in the constructor state (octree.h:71-74): nothing is loaded
+B2_HD int fresh_leaf_store (const Params& p, const Frame& f, const NodePos& n, const Obs& o, Counters& cnt)
 {
-  cnt.n_visits++;
-  if (!o.valid) return 0;
-  if (o.near_ && n.size > p.finest_size)
-  {
-    uint32_t smask = 0; uint32_t* sw = split_word (p, n, smask);
-    if (split_and_expand (p, f, n, sw, smask, cnt)) return 1;
-  }
-  // leaf update of a node known to be in the constructor state (octree.h:71-74)
   float2 dw = make_float2 (-1.f, 0.f); uchar4 c = make_uchar4 (0, 0, 0, 0); float M = 0.f; int ns = 0;
   bool updated;
   int rc = leaf_update_values (p, f, o, dw, c, M, ns, updated);
@@ -577,6 +570,18 @@ B2_HDN inline int visit_fresh_leaf (const Params& p, const Frame& f, const NodeP
     }
   }
   return rc;
+}
+
+B2_HDN inline int visit_fresh_leaf (const Params& p, const Frame& f, const NodePos& n, const Obs& o, Counters& cnt)
+{
+  cnt.n_visits++;
+  if (!o.valid) return 0;
+  if (o.near_ && n.size > p.finest_size)
+  {
+    uint32_t smask = 0; uint32_t* sw = split_word (p, n, smask);
+    if (split_and_expand (p, f, n, sw, smask, cnt)) return 1;
+  }
+  return fresh_leaf_store (p, f, n, o, cnt);
 }
 
 // returns true if the node stays split (some child is non-empty), false if the children were pruned again
@@ -599,6 +604,113 @@ B2_HDN inline bool split_and_expand (const Params& p, const Frame& f, const Node
   return false;
 }
 
+// ---- the same visit of a FRESH subtree, breadth first and cooperative --------------------------------------------
+// A node whose pre-existing children were pruned is visited as a leaf and may split again; everything
+// below it is then in the constructor state and the visit is a pure function of the frame.  The depth-first routine
+// above makes one lane walk the whole subtree; this one keeps the subtree as an array of records (creation order =
+// breadth first, a node's eight children adjacent) so that `nlanes` lanes visit a whole level together, then folds
+// the return codes level by level from the bottom.  Nodes that do not fit in the record array are walked depth
+// first by the lane that reached them.  The result (tree, values, counters) is identical to the recursion's.
+struct FreshRec { NodePos n; float dnew; int uv; short first; signed char rc; unsigned char state; };
+enum { FR_LEAF = 0, FR_INTERNAL = 1 };
+struct CoopSingle { B2_HD int lane () const { return 0; } B2_HD int nlanes () const { return 1; } B2_HD void sync () const {} };
+
+B2_HD int atomic_add_int (int* a, int v)
+{
+#ifdef __CUDA_ARCH__
+  return atomicAdd (a, v);
+#else
+  int o = *a; *a = o + v; return o;
+#endif
+}
+
+// n has just been split (split bit set, children storage cs, all fresh).  rec: cap records (cap a multiple of 8, >= 8),
+// counter: one int, both shared by the cooperating lanes.  Returns true if some child is non-empty (n stays split);
+// otherwise the caller clears n's children (rec[0..7].n) and updates n as a leaf.
+template <typename Coop>
+B2_HDN inline bool fresh_children_bfs (const Params& p, const Frame& f, const NodePos& n, int cs, FreshRec* rec, int cap, int* counter,
+                                       const Coop& co, Counters& cnt)
+{
+  const int lane = co.lane (), nl = co.nlanes ();
+  for (int c = lane; c < 8; c += nl) rec[c].n = make_child (p, n, c, cs);
+  int lev_lo[24]; int nlev = 0;
+  int lo = 0, hi = 8;
+  co.sync ();
+  while (lo < hi)
+  {
+    lev_lo[nlev++] = lo;
+    if (lane == 0) *counter = hi;
+    co.sync ();
+    for (int i = lo + lane; i < hi; i += nl)
+    {
+      const NodePos q = rec[i].n;
+      cnt.n_visits++;
+      const Obs o = observe (p, f, q.cx, q.cy, q.cz, q.size);
+      int rc = 0; unsigned char st = FR_LEAF;
+      if (o.valid)
+      {
+        bool handled = false;
+        if (o.near_ && q.size > p.finest_size)
+        {
+          const int cs2 = children_slot (p, q, true);
+          if (cs2 >= 0)
+          {
+            const int base = atomic_add_int (counter, 8);
+            if (base + 8 <= cap)
+            {
+              uint32_t m = 0; uint32_t* sw = split_word (p, q, m);
+              atomic_or32 (sw, m);                                     // split (): the children are fresh by invariant
+              for (int c = 0; c < 8; ++c) rec[base + c].n = make_child (p, q, c, cs2);
+              st = FR_INTERNAL; rec[i].first = (short) base; rec[i].dnew = o.d_new; rec[i].uv = o.u | (o.v << 16);
+            }
+            else
+            {
+              cnt.n_visits--;                                          // visit_fresh_leaf counts the node itself
+              rc = visit_fresh_leaf (p, f, q, o, cnt);                 // no room for its children: depth first from here
+            }
+            handled = true;
+          }
+        }
+        if (!handled) rc = fresh_leaf_store (p, f, q, o, cnt);
+      }
+      rec[i].rc = (signed char) rc; rec[i].state = st;
+    }
+    co.sync ();
+    const int total = *counter;
+    const int room = hi + ((cap - hi) / 8) * 8;                        // allocations beyond the array were refused
+    lo = hi;
+    hi = total < room ? total : room;
+    co.sync ();
+  }
+  const int end = lo;
+  for (int L = nlev - 1; L >= 0; --L)                                  // hpp:176-188 + fall-through, deepest level first
+  {
+    const int a = lev_lo[L], b = (L + 1 < nlev) ? lev_lo[L + 1] : end;
+    for (int i = a + lane; i < b; i += nl)
+    {
+      if (rec[i].state != FR_INTERNAL) continue;
+      const int first = rec[i].first;
+      bool any = false;
+      for (int c = 0; c < 8; ++c) any |= rec[first + c].rc >= 0;
+      if (any) { rec[i].rc = 1; continue; }
+      const NodePos q = rec[i].n;
+      uint32_t m = 0; uint32_t* sw = split_word (p, q, m);
+      atomic_and32 (sw, ~m);                                           // children.clear ()
+      for (int c = 0; c < 8; ++c) reset_node (p, rec[first + c].n);
+      Obs o; o.valid = true; o.near_ = true; o.d_new = rec[i].dnew; o.u = rec[i].uv & 0xFFFF; o.v = rec[i].uv >> 16;
+      rec[i].rc = (signed char) fresh_leaf_store (p, f, q, o, cnt);
+    }
+    co.sync ();
+  }
+  bool any = false;
+  for (int c = 0; c < 8; ++c) any |= rec[c].rc >= 0;
+  return any;
+}
+
+#if defined(B2_EMU_BFS) && !defined(__CUDACC__)
+extern int b2_emu_bfs_cap;               // tests/emu/emu.cpp: record capacity for the host emulation (0 = recursion only)
+#endif
+
 B2_HDN inline int update_voxel_dfs (const Params& p, const Frame& f, const NodePos& n, Counters& cnt)
 {
   cnt.n_visits++;
@@ -618,7 +730,25 @@ B2_HDN inline int update_voxel_dfs (const Params& p, const Frame& f, const NodeP
   Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
   if (!o.valid) return 0;
   if (o.near_ && n.size > p.finest_size)                         // hpp:161-188
+  {
+#if defined(B2_EMU_BFS) && !defined(__CUDACC__)
+    if (b2_emu_bfs_cap >= 8)
+    {
+      // host emulation of the cooperative routine (one "lane"): every split in the emulated frame goes through it
+      static thread_local FreshRec recs[1024];
+      int cs = children_slot (p, n, true), counter = 0;
+      if (cs >= 0)
+      {
+        atomic_or32 (sw, smask);
+        if (fresh_children_bfs (p, f, n, cs, recs, b2_emu_bfs_cap, &counter, CoopSingle (), cnt)) return 1;
+        atomic_and32 (sw, ~smask);
+        for (int c = 0; c < 8; ++c) reset_node (p, recs[c].n);
+      }
+    }
+    else
+#endif
     if (split_and_expand (p, f, n, sw, smask, cnt)) return 1;
+  }
   bool updated;
   int rc = leaf_update (p, f, n, o, updated);
   if (updated) cnt.n_updates++;

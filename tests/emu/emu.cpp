@@ -6,6 +6,7 @@
 // loop.  The not-gpu tests compare it with the oracle to validate the flat layout, the hash
 // directory and the per-node arithmetic before any GPU time is spent.  It is NOT part of the
 // product: libb200tsdf.so has no CPU path and nothing in cpu_tsdf_b200/ loads this library.
+#define B2_EMU_BFS 1
 #include "../../cpu_tsdf_b200/csrc/tsdf_core.cuh"
 #include "../../cpu_tsdf_b200/csrc/organize.cuh"
 #include "../../cpu_tsdf_b200/csrc/meshpost_core.cuh"
@@ -14,10 +15,15 @@
 #include "../../oracle/mc_tables.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 using namespace b2;
+
+// record capacity of the breadth-first fresh-subtree visit in the emulated frames (B2_EMU_BFS_CAP: 0 = recursion only,
+// 8..1024 = every split goes through fresh_children_bfs with that many records; small values exercise the overflow path)
+namespace b2 { int b2_emu_bfs_cap = 128; }
 
 struct Emu
 {
@@ -66,6 +72,7 @@ void emu_destroy (Emu* e) { delete e; }
 
 int emu_reset (Emu* e)
 {
+  if (const char* c = std::getenv ("B2_EMU_BFS_CAP")) b2_emu_bfs_cap = std::min (1024, std::atoi (c) / 8 * 8);
   size_t pool, root_n;
   if (derive_params (e->cfg, e->p, pool, root_n)) return -1;
   Params& p = e->p;

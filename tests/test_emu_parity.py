@@ -133,3 +133,17 @@ def test_global_transform_applies_to_mesh_only():
     assert_same_nodes(o.dump_nodes(), e.dump_nodes())
     va, _ = o.mesh(1.0, 0); vb, _ = e.mesh(1.0, 0)
     assert len(va) > 1000 and np.array_equal(canon_soup(va), canon_soup(vb))
+
+
+@pytest.mark.parametrize("cap", ["0", "16", "128"])
+def test_breadth_first_fresh_subtree_visit_equals_the_recursion(cap, monkeypatch):
+    """fresh_children_bfs (the cooperative re-split visit of k_celltop_up) driven by one emulated lane for EVERY split of
+    the frame: record capacity 128, 16 (most subtrees overflow into the depth-first fallback) and 0 (recursion only)."""
+    monkeypatch.setenv("B2_EMU_BFS_CAP", cap)
+    o, e = pair(CFG_256, integrate_color=1)
+    for pose, cloud in frames(synth.S1, 6, stride=9, color=True, noise_seed=11):
+        o.integrate(cloud, pose); e.integrate(cloud, pose)
+    assert_same_nodes(o.dump_nodes(), e.dump_nodes(), rgb=True)
+    so, se = o.stats(), e.stats()
+    assert so.n_add_observation == se["n_updates"] and so.n_node_visits == se["n_visits"]
+    monkeypatch.setenv("B2_EMU_BFS_CAP", "128")
