@@ -261,7 +261,7 @@ extern "C" int b200tsdf_mesh_flatten (int device, const float* verts, size_t nve
   if (nt) MCK (cudaMemcpyAsync (d_tris, tris, ntris * 12, cudaMemcpyHostToDevice, B.s));
   MCK (cudaMemsetAsync (state, FV_UNDECIDED, std::max<size_t> (nverts, 1), B.s));
   // pcl::search::KdTree::radiusSearch (i, min_dist): FLANN compares squared float distances with float (radius*radius)
-  const float r2 = (float) ((double) min_dist * (double) min_dist);
+  const float r2 = min_dist > 0.f ? (float) ((double) min_dist * (double) min_dist) : 0.f;      // radius <= 0 (or NaN): nothing is in range
   PointGrid g{};
   if ((rc = build_grid (B, g, d_verts, nv, std::max ((double) min_dist * 1.001, 1e-7)))) return rc;
   int left = nv;
@@ -317,7 +317,7 @@ extern "C" int b200tsdf_mesh_cleanup (int device, const float* verts, size_t nve
   if (nt)
   {
     // EuclideanClusterExtraction::setClusterTolerance (face_dist): radiusSearch with float (tolerance * tolerance)
-    const float r2 = (float) ((double) face_dist * (double) face_dist);
+    const float r2 = face_dist > 0.f ? (float) ((double) face_dist * (double) face_dist) : 0.f;
     k_cm_centroids<<<nblk (nt), TPB, 0, B.s>>> (d_verts, d_tris, nt, cent);
     PointGrid g{};
     if ((rc = build_grid (B, g, cent, nt, std::max ((double) face_dist * 1.001, 1e-7)))) return rc;

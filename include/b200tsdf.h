@@ -148,6 +148,12 @@ int  b200tsdf_mesh_cleanup (int device, const float* verts, size_t nverts, const
 void b200tsdf_mesh_free (void* p);
 const char* b200tsdf_meshpost_last_error (void);   /* thread-local message of the last failed call above */
 
+/* Diagnostics: per-phase timing of the bottom-up per-cell kernel (k_celltop_up).  The first call arms the counters,
+ * every call returns and clears them: out16[0..5] = max SM cycles << 32 | tag (total, level-3, level-2, level-1, cell,
+ * wait before the first cell), out16[6..10] = slow level-2 nodes, slow level-1 nodes, cell leaf visits, cell
+ * fall-throughs, cells folded.  Used by tools/dbg_celltop.py; not needed for normal operation. */
+int  b200tsdf_debug_timing (b200tsdf_t* h, unsigned long long* out16);
+
 /* TSDFVolumeOctree::save (cpp:222-245): reference-compatible .vol */
 int  b200tsdf_save (b200tsdf_t* h, const char* path);
 

@@ -44,7 +44,7 @@ struct RadiusSearch
   RadiusSearch (const float* p, size_t n_, float radius) : pts (p), n (n_)
   {
     cell = std::max (radius * 1.01f, 1e-6f);
-    r2 = static_cast<float> (static_cast<double> (radius) * static_cast<double> (radius));
+    r2 = radius > 0.f ? static_cast<float> (static_cast<double> (radius) * static_cast<double> (radius)) : 0.f;   // no radius, no neighbours
     buckets.reserve (n * 2);
     for (size_t i = 0; i < n; ++i)
       buckets[key (c1 (p[3 * i], cell), c1 (p[3 * i + 1], cell), c1 (p[3 * i + 2], cell))].push_back (static_cast<int> (i));

@@ -323,7 +323,7 @@ extern "C" void emu_mesh_flatten (const float* verts, size_t nverts, const int32
                                   float* out_verts, size_t* out_nverts, int32_t* out_tris, size_t* out_ntris, int* rounds_out)
 {
   int nv = (int) nverts;
-  const float r2 = (float) ((double) min_dist * (double) min_dist);
+  const float r2 = min_dist > 0.f ? (float) ((double) min_dist * (double) min_dist) : 0.f;
   HostGrid G (verts, nv, std::max ((double) min_dist * 1.001, 1e-7));
   std::vector<unsigned char> state (std::max (nv, 1), FV_UNDECIDED);
   int rounds = 0;
@@ -351,7 +351,7 @@ extern "C" void emu_mesh_cleanup (const float* verts, size_t nverts, const int32
                                   float* out_verts, size_t* out_nverts, int32_t* out_tris, size_t* out_ntris)
 {
   int nt = (int) ntris;
-  const float r2 = (float) ((double) face_dist * (double) face_dist);
+  const float r2 = face_dist > 0.f ? (float) ((double) face_dist * (double) face_dist) : 0.f;
   std::vector<float> cent (3 * std::max<size_t> (ntris, 1));
   for (int t = nt; t-- > 0;) face_centroid (verts, tris + 3 * (size_t) t, cent.data () + 3 * (size_t) t);
   HostGrid G (cent.data (), nt, std::max ((double) face_dist * 1.001, 1e-7));

@@ -108,6 +108,12 @@ def test_flatten_then_cleanup_and_empty_meshes(soup):
     e = (np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
     for mod in (oracle_py, emu_py):
         assert mod.flatten_vertices(*e)[0].shape == (0, 3) and mod.cleanup_mesh(*e)[1].shape == (0, 3)
+        # a zero or negative radius finds no neighbours: nothing is welded (exact duplicates included), and every face is its
+        # own cluster of one, so cleanupMesh removes them all
+        for r in (0.0, -1.0):
+            fv = mod.flatten_vertices(v[:3000], t[:1000] % 3000, r)
+            assert len(fv[0]) == 3000
+            assert len(mod.cleanup_mesh(v[:300], np.arange(300, dtype=np.int32).reshape(-1, 3), r)[1]) == 0
 
 
 # ---------------------------------------------------------------------------------------------------------
