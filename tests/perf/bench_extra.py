@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Secondary measurements (not the BASELINE metric): renderView and marching-cubes time on the GPU vs
 the CPU reference, on BASELINE.json configs[1] (512^3 orbit) and configs[2] (2048^3 interior, colour).
-Prints one JSON line per config.  Usage: python tools/bench_extra.py [--frames N] [--no-cpu]"""
+Prints one JSON line per config.  Usage: python tests/perf/bench_extra.py [--frames N] [--no-cpu]"""
 import argparse
 import json
 import os
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import cpu_tsdf_b200 as pkg  # noqa: E402
 from cpu_tsdf_b200 import synth  # noqa: E402
