@@ -40,14 +40,6 @@ constexpr int KRING = 64;     // ring of event pairs around the dominant kernel
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-// start of a frame: snapshot the cumulative counters, clear the work-list counts
-__global__ void k_frame_begin (unsigned long long* __restrict__ stats, int* __restrict__ counts)
-{
-  int i = threadIdx.x;
-  if (i < ST_N) stats[ST_N + i] = stats[i];
-  if (i < 16) counts[i] = 0;
-}
-
 __global__ void k_fill_fresh (float2* __restrict__ nodes, size_t n)
 {
   size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,27 +55,6 @@ __global__ void k_insert_top_bricks (Params p)
   if (i >= n * n * n) return;
   int z = i % n, y = (i / n) % n, x = i / (n * n);
   find_or_insert_brick (p, p.T - 1, x, y, z);
-}
-
-// pre-split (hpp:56-90): one thread per depth pixel
-__global__ void k_presplit (Params p, Frame f)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= f.width * f.height) return;
-  int u = i % f.width, v = i / f.width;
-  const float* pt = frame_xyz (f, u, v);
-  float z = pt[2];
-  if (is_nan (z)) return;                                        // hpp:64
-  float pw[3];
-  affine_mul_f (f.tfwd, pt[0], pt[1], z, pw);                    // hpp:76
-  int fx_, fy_, fz_;
-  if (!world_to_finest (p, pw[0], pw[1], pw[2], fx_, fy_, fz_)) return;
-  if (p.shard_count > 1)
-  {
-    int sh = p.L - p.C;
-    if (!owns_cell (p, fx_ >> sh, fy_ >> sh, fz_ >> sh)) return;
-  }
-  presplit_point (p, fx_, fy_, fz_);
 }
 
 // frustum cull of the coarse cells (tsdf_volume_octree.cpp:619-652); planes come from the host
@@ -112,7 +83,7 @@ __global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restr
 
 // frame front end in ONE launch: blocks [0, cull_blocks) run the frustum cull of the coarse cells, the
 // rest the per-pixel pre-split.  The two are independent (the cull reads only geometry).  The work-list
-// counters and the statistics snapshot are reset by k_frame_begin on the previous launch boundary.
+// counters and the statistics snapshot are reset by the frame-begin bookkeeping of the previous k_front launch.
 __global__ void k_front (Params p, Frame f, Planes P, int cull_blocks, int* __restrict__ list, int* __restrict__ count, QNode* __restrict__ q0,
                          unsigned long long* __restrict__ stats, int* __restrict__ next_counts)
 {

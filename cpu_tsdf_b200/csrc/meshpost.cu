@@ -57,11 +57,6 @@ __global__ void k_grid_insert (PointGrid g, int n)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) grid_insert (g, i);
 }
-__global__ void k_fill_i32 (int* a, int v, size_t n)
-{
-  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] = v;
-}
 __global__ void k_iota (int* a, int n)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
