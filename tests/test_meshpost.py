@@ -116,6 +116,17 @@ def test_flatten_then_cleanup_and_empty_meshes(soup):
             assert len(mod.cleanup_mesh(v[:300], np.arange(300, dtype=np.int32).reshape(-1, 3), r)[1]) == 0
 
 
+def test_post_processing_has_no_cpu_path():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import cpu_tsdf_b200 as pkg
+    v = np.zeros((3, 3), np.float32); t = np.arange(3, dtype=np.int32).reshape(1, 3)
+    for fn in (pkg.flattenVertices, pkg.cleanupMesh):
+        with pytest.raises(pkg.B200Error, match="no such CUDA device"):
+            fn(v, t)
+
+
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_cuda_flatten_and_cleanup_match_the_restatement(soup):
