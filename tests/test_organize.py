@@ -57,6 +57,41 @@ def test_emulated_device_code_matches_the_restatement(color):
     assert same_cloud(want[..., :3], got16[..., :3]) and same_cloud(want[..., 4], got16[..., 3])
 
 
+def numpy_organize(pts, intr, W, H, cloud_units=1.0, zero_nans=False):
+    """An independent, vectorised statement of integrate.cpp:548-607 (no world transform): per pixel the accepted point with
+    the smallest (z, input index)."""
+    fx, fy, cx, cy = np.float32(intr)
+    xyz = pts[:, :3].astype(np.float32).copy()
+    if cloud_units != 1.0:
+        xyz *= np.float32(cloud_units)
+    if zero_nans:
+        xyz[(xyz == 0).all(1)] = np.nan
+    x, y, z = xyz.T
+    with np.errstate(all="ignore"):
+        fu = (x * fx / z + cx).astype(np.float32); fv = (y * fy / z + cy).astype(np.float32)
+        okf = np.isfinite(fu) & np.isfinite(fv) & (np.abs(fu) < 2e9) & (np.abs(fv) < 2e9)
+        u = np.where(okf, np.trunc(np.where(okf, fu, 0)), -1).astype(np.int64); v = np.where(okf, np.trunc(np.where(okf, fv, 0)), -1).astype(np.int64)
+        ok = okf & ~np.isnan(z) & (z > 0) & (u >= 0) & (u < W) & (v >= 0) & (v < H)
+    idx = np.nonzero(ok)[0]
+    pix = v[idx] * W + u[idx]
+    order = np.lexsort((idx, z[idx], pix))                       # by pixel, then z, then input order
+    first = np.ones(len(order), bool); first[1:] = pix[order][1:] != pix[order][:-1]
+    win = idx[order][first]; wpix = pix[order][first]
+    out = np.zeros((H * W, 8), np.float32); out[:, 2] = np.nan; out[:, 3] = 1.0
+    out[:, 4] = np.array([0, 0, 0, 255], np.uint8).view(np.float32)[0]
+    out[wpix, :3] = xyz[win]
+    out[wpix, 4] = pts[win, 4]
+    return out.reshape(H, W, 8), len(win)
+
+
+def test_restatement_agrees_with_an_independent_vectorised_statement():
+    for seed, kw, gen in [(1, {}, {}), (4, dict(cloud_units=0.001, zero_nans=True), dict(scale=0.001))]:
+        pts, _ = unorganized_cloud(seed, **gen)
+        a, na = oracle_py.organize(pts, INTR, CAM.width, CAM.height, rgba_off=16, **kw)
+        b, nb = numpy_organize(pts, INTR, CAM.width, CAM.height, **kw)
+        assert na == nb and same_cloud(a, b)
+
+
 def test_units_zero_nans_and_world_frame_options():
     from tests.emu import emu_py
     world = synth.orbit_pose(synth.S1, 17, 100)
