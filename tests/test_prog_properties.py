@@ -67,3 +67,68 @@ def test_cleanup_random_meshes(mesh, d, k):
     v, t = mesh
     a = oracle_py.cleanup_mesh(v, t, d, k); b = emu_py.cleanup_mesh(v, t, d, k)
     assert a[0].shape == b[0].shape and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
+
+
+# ---- independent brute-force statements (no search structure at all) ------------------------------------------------
+def sqdist_f32(v):
+    d = v[:, None, :] - v[None, :, :]
+    q = (d * d).astype(np.float32)
+    return ((q[..., 0] + q[..., 1]).astype(np.float32) + q[..., 2]).astype(np.float32)
+
+
+def brute_flatten(v, t, r):
+    """integrate.cpp:103-150 transcribed literally, radiusSearch = all j != i with float squared distance < float(r*r)."""
+    n = len(v)
+    r2 = np.float32(float(np.float32(r)) ** 2) if r > 0 else np.float32(0)
+    near = sqdist_f32(v) < r2 if n else np.zeros((0, 0), bool)
+    remap = [-1] * n; new = []
+    for i in range(n):
+        if remap[i] >= 0:
+            continue
+        remap[i] = len(new)
+        for j in range(n):
+            if j != i and near[i, j]:
+                remap[j] = len(new)
+        new.append(v[i])
+    faces = []
+    for a, b, c in t:
+        a, b, c = remap[a], remap[b], remap[c]
+        if a == b or b == c or c == a:
+            continue
+        faces.append((a, b, c))
+    return np.float32(new).reshape(-1, 3), np.int32(faces).reshape(-1, 3)
+
+
+def brute_cleanup(v, t, d, k):
+    """integrate.cpp:152-214 with scipy's connected components as the cluster extraction."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    m = len(t)
+    if m == 0:
+        return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32)
+    c = ((v[t[:, 0]] + v[t[:, 1]]).astype(np.float32) + v[t[:, 2]]).astype(np.float32) / np.float32(3)
+    r2 = np.float32(float(np.float32(d)) ** 2)
+    adj = sqdist_f32(c.astype(np.float32)) < r2
+    np.fill_diagonal(adj, False)
+    _, lab = connected_components(csr_matrix(adj), directed=False)
+    size = np.bincount(lab)[lab]
+    keep = size > k
+    tt = t[keep]
+    used = np.zeros(len(v), bool); used[tt.reshape(-1)] = True
+    newidx = np.cumsum(used) - 1
+    return v[used], newidx[tt].astype(np.int32).reshape(-1, 3)
+
+
+@settings(max_examples=60, deadline=None)
+@given(meshes(), st.sampled_from([1e-4, 5e-5]))
+def test_flatten_restatement_agrees_with_a_literal_brute_force_transcription(mesh, r):
+    a = oracle_py.flatten_vertices(*mesh, r); b = brute_flatten(*mesh, r)
+    assert a[0].shape == b[0].shape and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
+
+
+@settings(max_examples=60, deadline=None)
+@given(meshes(), st.sampled_from([0.02, 0.005, 0.08]), st.integers(1, 8))
+def test_cleanup_restatement_agrees_with_connected_components(mesh, d, k):
+    v, t = mesh
+    a = oracle_py.cleanup_mesh(v, t, d, k); b = brute_cleanup(v, t, d, k)
+    assert a[0].shape == b[0].shape and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
