@@ -27,6 +27,7 @@ class OrcConfig(C.Structure):
         ("image_width", C.c_int32), ("image_height", C.c_int32),
         ("integrate_color", C.c_int32), ("num_threads", C.c_int32),
         ("global_transform", C.c_double * 16),
+        ("color_mode", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -74,6 +75,7 @@ def load(kind: str = "port") -> C.CDLL:
     lib.orc_voxel_center.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp]
     lib.orc_voxel_index.argtypes = [vp, C.c_float, C.c_float, C.c_float, vp]
     lib.orc_frustum_cull.argtypes = [vp, vp, vp]
+    lib.orc_dump_color_payload.argtypes = [vp, vp]; lib.orc_dump_color_payload.restype = C.c_int64
     if kind == "port":               # the program-side restatement (oracle/prog_oracle.cpp) exists in the port only
         lib.orc_organize.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
         lib.orc_organize.restype = C.c_int64
@@ -183,7 +185,12 @@ class OracleVolume:
         keys = np.empty((n, 4), np.int32); dw = np.empty((n, 2), np.float32); flags = np.empty(n, np.uint8)
         rgb = np.empty((n, 3), np.uint8); M = np.empty(n, np.float32); ns = np.empty(n, np.int32)
         self.lib.orc_dump_nodes(self.h, _ptr(keys), _ptr(dw), _ptr(flags), _ptr(rgb), _ptr(M), _ptr(ns))
-        return {"keys": keys, "dw": dw, "split": flags, "rgb": rgb, "M": M, "ns": ns}
+        out = {"keys": keys, "dw": dw, "split": flags, "rgb": rgb, "M": M, "ns": ns}
+        if self.cfg.integrate_color and self.cfg.color_mode == 1:
+            payload = np.zeros((n, 4), np.float32)                 # RGBNormalized: r_n_, g_n_, b_n_, i_
+            assert self.lib.orc_dump_color_payload(self.h, _ptr(payload)) == n
+            out["rgbn"] = payload
+        return out
 
     def voxel_center(self, x, y, z):
         o = np.empty(3, np.float32)

@@ -86,6 +86,7 @@ int orc_reset (orc_volume* v)
   t.setCameraIntrinsics (c.fx, c.fy, c.cx, c.cy);
   t.setMaxVoxelSize (c.max_cell_x, c.max_cell_y, c.max_cell_z);
   t.setIntegrateColor (c.integrate_color != 0);
+  t.setColorMode (c.color_mode == 1 ? "RGBNormalized" : "RGB");
   t.setGlobalTransform (to_affine (c.global_transform));
 #ifdef _OPENMP
   if (c.num_threads > 0) omp_set_num_threads (c.num_threads);
@@ -233,6 +234,20 @@ int64_t orc_dump_nodes (const orc_volume* v, int32_t* keys, float* dw, uint8_t* 
     }
     if (M) M[i] = n->M_;
     if (ns) ns[i] = n->nsample_;
+  }
+  return static_cast<int64_t> (recs.size ());
+}
+
+int64_t orc_dump_color_payload (const orc_volume* v, float* out4)
+{
+  std::vector<Rec> recs; int64_t total = 0;
+  collect (v->tsdf->octree_->getRoot ().get (), 0, 0, 0, 0, v->num_levels, recs, total);
+  if (recs.empty () || !dynamic_cast<const cpu_tsdf::RGBNormalized*> (recs[0].n)) return 0;
+  std::sort (recs.begin (), recs.end (), [] (const Rec& a, const Rec& b) { return std::lexicographical_compare (a.k, a.k + 4, b.k, b.k + 4); });
+  for (size_t i = 0; i < recs.size (); ++i)
+  {
+    const cpu_tsdf::RGBNormalized* n = dynamic_cast<const cpu_tsdf::RGBNormalized*> (recs[i].n);
+    out4[4 * i] = n->r_n_; out4[4 * i + 1] = n->g_n_; out4[4 * i + 2] = n->b_n_; out4[4 * i + 3] = n->i_;
   }
   return static_cast<int64_t> (recs.size ());
 }

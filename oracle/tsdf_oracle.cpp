@@ -39,6 +39,7 @@ struct Node
   int32_t child;            // index of children_[0]; -1 = no children
   int32_t ix, iy, iz;       // integer coordinates at this node's own level (bookkeeping only)
   uint8_t level, r, g, b;
+  float rn, gn, bn, in;     // RGBNormalized payload (octree.h:250-253)
 };
 
 constexpr int CHUNK_BITS = 20;
@@ -110,6 +111,7 @@ struct orc_volume
   int finest_level = 0;
   bool is_empty = true;
   bool color = false;          // node type "RGB" iff integrate_color_ at reset (cpp:206-209)
+  bool rgbn = false;           // node type "RGBNormalized" (setColorMode, h:290)
   std::vector<int32_t> coarse; // getLeaves(max_cell...) result (depth == num_levels), DFS order
   orc_stats stats{};
   PerThread pt[MAX_THREADS];
@@ -123,6 +125,7 @@ struct orc_volume
     n.cx = x; n.cy = y; n.cz = z; n.size = size;
     n.child = -1; n.ix = ix; n.iy = iy; n.iz = iz; n.level = static_cast<uint8_t> (level);
     n.r = n.g = n.b = 0;
+    n.rn = n.gn = n.bn = n.in = 0;                               // octree.h:217-223
   }
 
   // ---- OctreeNode::split, octree.cpp:244-266 ------------------------------------------
@@ -218,7 +221,20 @@ struct orc_volume
   // ---- OctreeNode::addObservation octree.cpp:152-163, RGBNode:: octree.cpp:328-337 -----
   void add_observation (Node& n, float d_new, float w_new, float max_weight, const uint8_t* bgr)
   {
-    if (color && bgr)
+    if (rgbn && bgr)                                              // RGBNormalized::addObservation, octree.cpp:380-393
+    {
+      uint8_t r = bgr[2], g = bgr[1], b = bgr[0];
+      float wsum = n.w + w_new;
+      float i = std::sqrt ((float) r * (float) r + (float) g * (float) g + (float) b * (float) b);
+      float r_f = r / i;
+      float g_f = g / i;
+      float b_f = b / i;
+      n.rn = (n.w * n.rn + w_new * r_f) / wsum;
+      n.gn = (n.w * n.gn + w_new * g_f) / wsum;
+      n.bn = (n.w * n.bn + w_new * b_f) / wsum;
+      n.in = (n.w * n.in + w_new * i) / wsum;
+    }
+    else if (color && bgr)
     {
       uint8_t r = bgr[2], g = bgr[1], b = bgr[0];
       float wsum = n.w + w_new;
@@ -232,6 +248,19 @@ struct orc_volume
     if (n.w > max_weight) n.w = max_weight;
     n.M += w_new * (d_new - n.d) * (d_new - d_old);
     ++n.ns;
+  }
+
+  // getRGB: RGBNode (octree.cpp:340-346) / RGBNormalized (octree.cpp:396-402: `r = r_n_ * i_`, a float -> uint8_t
+  // conversion, which x86-64 compiles to cvttss2si + a byte truncation)
+  static uint8_t f2u8 (float v)
+  {
+    int32_t t = (v >= -2147483648.f && v < 2147483648.f) ? static_cast<int32_t> (v) : INT32_MIN;
+    return static_cast<uint8_t> (t);
+  }
+  void get_rgb (const Node& n, uint8_t& r, uint8_t& g, uint8_t& b) const
+  {
+    if (rgbn) { r = f2u8 (n.rn * n.in); g = f2u8 (n.gn * n.in); b = f2u8 (n.bn * n.in); }
+    else { r = n.r; g = n.g; b = n.b; }
   }
 
   // ---- frame view ------------------------------------------------------------------------
@@ -394,6 +423,7 @@ void orc_default_config (orc_config* c)
   c->image_width = 640; c->image_height = 480;
   c->max_cell_x = c->max_cell_y = c->max_cell_z = 0.5f;
   c->integrate_color = 0;
+  c->color_mode = 0; c->reserved_ = 0;
   c->num_threads = 0;
   for (int i = 0; i < 4; ++i) c->global_transform[i * 5] = 1.0;
 }
@@ -414,6 +444,7 @@ int orc_reset (orc_volume* v)
   v->pool.clear ();
   v->is_empty = true;
   v->color = c.integrate_color != 0;
+  v->rgbn = v->color && c.color_mode == 1;
   v->root = v->pool.alloc (1, 0);
   v->init_node (v->pool.at (v->root), 0, 0, 0, c.xsize, 0, 0, 0, 0);   // size_ = size_x (octree.h:67)
   int desired_res = std::max (c.xsize / c.max_cell_x, std::max (c.ysize / c.max_cell_y, c.zsize / c.max_cell_z));
@@ -673,7 +704,7 @@ int orc_render (const orc_volume* v, const double* pose, int downsampleBy, void*
       if (ni >= 0)
       {
         const Node& n = v->pool.at (ni);
-        if (v->color) { rgb_out[3 * i] = n.r; rgb_out[3 * i + 1] = n.g; rgb_out[3 * i + 2] = n.b; }
+        if (v->color) v->get_rgb (n, rgb_out[3 * i], rgb_out[3 * i + 1], rgb_out[3 * i + 2]);
         else rgb_out[3 * i] = rgb_out[3 * i + 1] = rgb_out[3 * i + 2] = 127;   // OctreeNode::getRGB, octree.cpp:173-178
       }
     }
@@ -770,7 +801,7 @@ struct MC
           g = 0;
           b = std::max (0., std::min ((std_dev) * 255., 255.));
         }
-        else if (color_mode == 1 && v->color) { r = n.r; g = n.g; b = n.b; }
+        else if (color_mode == 1 && v->color) v->get_rgb (n, r, g, b);
         col.push_back (r); col.push_back (g); col.push_back (b);
       }
   }
@@ -809,7 +840,9 @@ std::string fmt16 (double x) { char b[64]; std::snprintf (b, sizeof (b), "%.16g"
 void write_node (const orc_volume* v, std::FILE* f, int32_t ni)
 {
   const Node& n = v->pool.at (ni);
-  if (v->color) { std::fwrite (&n.r, 1, 1, f); std::fwrite (&n.g, 1, 1, f); std::fwrite (&n.b, 1, 1, f); }
+  // RGBNormalized::serialize (octree.cpp:417-424) writes sizeof (uint8_t) = the FIRST BYTE of each of its four floats
+  if (v->rgbn) { std::fwrite (&n.rn, 1, 1, f); std::fwrite (&n.gn, 1, 1, f); std::fwrite (&n.bn, 1, 1, f); std::fwrite (&n.in, 1, 1, f); }
+  else if (v->color) { std::fwrite (&n.r, 1, 1, f); std::fwrite (&n.g, 1, 1, f); std::fwrite (&n.b, 1, 1, f); }
   std::fwrite (&n.d, 4, 1, f); std::fwrite (&n.w, 4, 1, f);
   std::fwrite (&n.cx, 4, 1, f); std::fwrite (&n.cy, 4, 1, f); std::fwrite (&n.cz, 4, 1, f);
   std::fwrite (&n.size, 4, 1, f); std::fwrite (&n.M, 4, 1, f); std::fwrite (&n.ns, 4, 1, f);
@@ -846,7 +879,7 @@ int orc_save (const orc_volume* v, const char* path)
     }
     h += "\n";
   }
-  h += std::string (v->color ? "RGB" : "NOCOLOR") + "\n#OCTREEBINARY\n";
+  h += std::string (v->rgbn ? "RGBNormalized" : (v->color ? "RGB" : "NOCOLOR")) + "\n#OCTREEBINARY\n";
   std::fwrite (h.data (), 1, h.size (), f);
   size_t res[3] = { (size_t) c.xres, (size_t) c.yres, (size_t) c.zres };
   std::fwrite (res, sizeof (size_t), 3, f);
@@ -881,9 +914,24 @@ int64_t orc_dump_nodes (const orc_volume* v, int32_t* keys, float* dw, uint8_t* 
     if (keys) std::memcpy (keys + 4 * i, recs[i].k, 16);
     if (dw) { dw[2 * i] = n.d; dw[2 * i + 1] = n.w; }
     if (flags) flags[i] = n.child >= 0;
-    if (rgb) { rgb[3 * i] = n.r; rgb[3 * i + 1] = n.g; rgb[3 * i + 2] = n.b; }
+    if (rgb) v->get_rgb (n, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
     if (M) M[i] = n.M;
     if (ns) ns[i] = n.ns;
+  }
+  return static_cast<int64_t> (recs.size ());
+}
+
+int64_t orc_dump_color_payload (const orc_volume* v, float* out4)
+{
+  if (!v->rgbn) return 0;
+  std::vector<Rec> recs;
+  collect (v, v->root, recs);
+  std::sort (recs.begin (), recs.end (), [] (const Rec& a, const Rec& b) {
+    return std::lexicographical_compare (a.k, a.k + 4, b.k, b.k + 4); });
+  for (size_t i = 0; i < recs.size (); ++i)
+  {
+    const Node& n = v->pool.at (recs[i].ni);
+    out4[4 * i] = n.rn; out4[4 * i + 1] = n.gn; out4[4 * i + 2] = n.bn; out4[4 * i + 3] = n.in;
   }
   return static_cast<int64_t> (recs.size ());
 }

@@ -34,6 +34,8 @@ typedef struct orc_config
   int32_t integrate_color;             /* setIntegrateColor (h:162); colour mode "RGB"  */
   int32_t num_threads;                 /* OpenMP threads for update/render; 0 = default */
   double global_transform[16];         /* setGlobalTransform (h:119), row-major 4x4     */
+  int32_t color_mode;                  /* setColorMode (h:290): 0 "RGB", 1 "RGBNormalized" (octree.cpp:378-433) */
+  int32_t reserved_;
 } orc_config;
 
 typedef struct orc_volume orc_volume;
@@ -86,6 +88,9 @@ int  orc_save (const orc_volume* v, const char* path);   /* cpp:222-245 */
 int64_t orc_dump_nodes (const orc_volume* v, int32_t* keys, float* dw, uint8_t* flags,
                         uint8_t* rgb, float* M, int32_t* ns);
 int  orc_levels (const orc_volume* v, int* coarse_level, int* finest_level);
+/* RGBNormalized payload (r_n_, g_n_, b_n_, i_: 4 floats per node) in the node order of orc_dump_nodes; returns the node
+ * count, or 0 when the volume does not use that node type */
+int64_t orc_dump_color_payload (const orc_volume* v, float* out4);
 
 /* helpers exposed for known-answer tests */
 void orc_voxel_center (const orc_volume* v, int64_t x, int64_t y, int64_t z, float* out3);      /* cpp:553 */

@@ -80,3 +80,34 @@ def test_cull_queries_render_mesh_vol(tmp_path):
     pa, pb = str(tmp_path / "a.vol"), str(tmp_path / "b.vol")
     a.save(pa); b.save(pb)
     assert open(pa, "rb").read() == open(pb, "rb").read()
+
+
+def test_rgb_normalized_voxels_match_the_reference(tmp_path):
+    """setColorMode("RGBNormalized") (tsdf_volume_octree.h:290, octree.cpp:378-433): normalised colour + intensity averages
+    per node, getRGB's float -> uint8 conversions, and the serializer that writes the first byte of each float.
+    (Restatement only so far: the CUDA engine implements colour mode "RGB".)"""
+    a, b = pair(CFG_256, integrate_color=1, color_mode=1)
+    for pose, cloud in frames(synth.S1, 5, stride=7, color=True, noise_seed=5):
+        a.integrate(cloud, pose); b.integrate(cloud, pose)
+    da, db = a.dump_nodes(), b.dump_nodes()
+    assert_same_nodes(da, db, rgb=True, var=True)
+    assert np.array_equal(da["rgbn"].view(np.uint32), db["rgbn"].view(np.uint32))
+    seen = da["dw"][:, 1] > 0
+    assert seen.sum() > 50000 and np.nanmax(da["rgbn"][seen][:, 3]) > 100        # intensities are accumulated
+    # unit colour direction wherever the pixel colour was not black (black gives 0/0 = NaN, as in the reference)
+    rgb_dir = da["rgbn"][seen][:, :3]; ok = np.isfinite(rgb_dir).all(1)
+    assert ok.sum() > 0.9 * seen.sum() and np.abs(np.linalg.norm(rgb_dir[ok], axis=1) - 1).max() < 0.2
+    pose = synth.orbit_pose(synth.S1, 10, 100)
+    ra, ca = a.render(pose, 4, colored=True); rb, cb = b.render(pose, 4, colored=True)
+    assert np.array_equal(ra[..., :3], rb[..., :3], equal_nan=True) and np.array_equal(ca, cb) and ca.any()
+    va, cola = a.mesh(0.0, 1); vb, colb = b.mesh(0.0, 1)
+    assert len(va) > 3000 and np.array_equal(va.view(np.uint32), vb.view(np.uint32)) and np.array_equal(cola, colb)
+    pa, pb = str(tmp_path / "a.vol"), str(tmp_path / "b.vol")
+    assert a.save(pa) == 0 and b.save(pb) == 0
+    ba, bb = open(pa, "rb").read(), open(pb, "rb").read()
+    assert ba == bb and b"RGBNormalized\n#OCTREEBINARY\n" in ba
+    # and the plain "RGB" mode is untouched by the new field
+    c, d = pair(CFG_256, integrate_color=1, color_mode=0)
+    pose, cloud = next(frames(synth.S1, 1, color=True))
+    c.integrate(cloud, pose); d.integrate(cloud, pose)
+    assert "rgbn" not in d.dump_nodes() and np.array_equal(c.dump_nodes()["rgb"], d.dump_nodes()["rgb"])
