@@ -27,3 +27,22 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_committed_gpu_bench_line_has_every_contract_key():
+    """profiles/r1_bench.json is the line `python bench.py` printed on the B200 box: check its shape against the contract."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "frames/s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "l2" in d["config"] and d["data"] == "synthetic" and d["dtype"] == "f32"
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    e = d["e2e"]
+    assert e["unit"] == "frames/s" and 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 32 * 640 * 480 * 32 and e["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "frames/s" and c["sample"]
+    assert d["gpu_launches"] == 4 * 32 * d["steps"]                      # four kernels per frame, 32 frames per step
+    assert abs(d["value"] - 32 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
