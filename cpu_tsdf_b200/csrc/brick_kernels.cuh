@@ -29,6 +29,15 @@ struct QNode
   int rc;             // updateVoxel return code
 };
 
+// one frame's parameters as the hot kernels read them (device memory: a captured launch can be replayed on another frame)
+struct FrameRec
+{
+  Frame f;
+  float pl[6][4];          // frustum planes (host_math.h)
+  int cset;                // which of the two per-frame counter sets this frame uses
+  int pad_[3];
+};
+
 constexpr int MAX_QLEVELS = 8;
 struct Queues
 {
@@ -977,14 +986,23 @@ __device__ __forceinline__ void top_kj (int f, int& k, int& j)
 { if (f == 0) { k = 0; j = 0; } else if (f < 9) { k = 1; j = f - 1; } else if (f < 73) { k = 2; j = f - 9; } else { k = 3; j = f - 73; } }
 
 template <bool COLOR>
-__global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, Frame f, const QNode* __restrict__ cells, const int* __restrict__ ncells,
+__global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const FrameRec* __restrict__ fr, const QNode* __restrict__ cells, int* __restrict__ d_count,
                                                                QNode* __restrict__ gq, CellTop* __restrict__ tops, int cell_cap,
-                                                               int* __restrict__ blist, int* __restrict__ bcount, unsigned long long* __restrict__ stats)
+                                                               int* __restrict__ blist, unsigned long long* __restrict__ stats)
 {
   __shared__ __align__ (16) TopSmem S;
+  __shared__ Frame s_f_;
   const int tid = threadIdx.x, lane = tid & 31;
+  {
+    const int* src_ = reinterpret_cast<const int*> (&fr->f); int* dst_ = reinterpret_cast<int*> (&s_f_);
+    for (int w_ = tid; w_ < (int) (sizeof (Frame) / sizeof (int)); w_ += TOP_THREADS) dst_[w_] = src_[w_];
+  }
+  int* const cnt_ = d_count + 16 * fr->cset;
+  int* const bcount = cnt_ + 9;
+  __syncthreads ();
+  const Frame& f = s_f_;
   unsigned long long upd = 0, vis = 0;
-  int count = *ncells;
+  int count = cnt_[0];
   if (count > cell_cap) { if (tid == 0 && blockIdx.x == 0) raise_err (p, ERR_QUEUE_FULL); count = cell_cap; }
   const float sizeC = level_size (p, p.C);
   const float off1 = sizeC * 0.25f;
@@ -1135,7 +1153,7 @@ __device__ __forceinline__ int top_fallthrough_new (const Params& p, const Frame
 }
 
 template <bool COLOR>
-__global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const QNode* __restrict__ cells, const int* __restrict__ ncells,
+__global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec* __restrict__ fr, const QNode* __restrict__ cells, const int* __restrict__ d_count,
                                                       const QNode* __restrict__ gq, const CellTop* __restrict__ tops, int cell_cap,
                                                       unsigned long long* __restrict__ stats)
 {
@@ -1148,7 +1166,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
   {
     const int* s1 = reinterpret_cast<const int*> (&gp); int* d1 = reinterpret_cast<int*> (&sp_);
     for (int w = threadIdx.x; w < (int) (sizeof (Params) / sizeof (int)); w += blockDim.x) d1[w] = s1[w];
-    const int* s2 = reinterpret_cast<const int*> (&gf); int* d2 = reinterpret_cast<int*> (&sf_);
+    const int* s2 = reinterpret_cast<const int*> (&fr->f); int* d2 = reinterpret_cast<int*> (&sf_);
     for (int w = threadIdx.x; w < (int) (sizeof (Frame) / sizeof (int)); w += blockDim.x) d2[w] = s2[w];
   }
   __syncthreads ();
@@ -1157,7 +1175,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, Frame gf, const
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   unsigned long long upd = 0, vis = 0;
-  int count = *ncells;
+  int count = d_count[16 * fr->cset];
   if (count > cell_cap) count = cell_cap;
   const float sizeC = level_size (p, p.C);
   const float off1 = sizeC * 0.25f;

@@ -8,6 +8,7 @@
 #include "host_math.h"
 #include "params_setup.h"
 #include "brick_kernels.cuh"
+#include "brick_direct.cuh"
 #include "organize.cuh"
 #include "mesh_sort.h"
 
@@ -36,6 +37,7 @@ struct Planes { float pl[6][4]; };
 // the current frame (so last-frame = cum - prev without a host round trip); the last slot is scratch
 enum StatSlot { ST_UPDATES = 0, ST_VISITS = 1, ST_BLOCKS = 2, ST_N = 8, ST_TOTAL = 2 * ST_N + 1, ST_SCRATCH = 2 * ST_N };
 constexpr int KRING = 64;     // ring of event pairs around the dominant kernel
+constexpr int FRAME_RING = 64;  // per-frame records in flight (device ring + its pinned host image)
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -84,9 +86,23 @@ __global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restr
 // frame front end in ONE launch: blocks [0, cull_blocks) run the frustum cull of the coarse cells, the
 // rest the per-pixel pre-split.  The two are independent (the cull reads only geometry).  The work-list
 // counters and the statistics snapshot are reset by the frame-begin bookkeeping of the previous k_front launch.
-__global__ void k_front (Params p, Frame f, Planes P, int cull_blocks, int* __restrict__ list, int* __restrict__ count, QNode* __restrict__ q0,
-                         unsigned long long* __restrict__ stats, int* __restrict__ next_counts)
+// The frame's parameters come from a record in device memory (FrameRec), so a captured launch can be replayed.
+#define B2_STAGE_FRAME(fr)                                                      \
+  __shared__ FrameRec s_fr_;                                                    \
+  {                                                                             \
+    const int* src_ = reinterpret_cast<const int*> (fr);                        \
+    int* dst_ = reinterpret_cast<int*> (&s_fr_);                                \
+    for (int w_ = threadIdx.x; w_ < (int) (sizeof (FrameRec) / sizeof (int)); w_ += blockDim.x) dst_[w_] = src_[w_]; \
+  }                                                                             \
+  __syncthreads ();                                                             \
+  const Frame& f = s_fr_.f;
+
+__global__ void k_front (Params p, const FrameRec* __restrict__ fr, int cull_blocks, int* __restrict__ list, int* __restrict__ d_count, QNode* __restrict__ q0,
+                         unsigned long long* __restrict__ stats)
 {
+  B2_STAGE_FRAME (fr)
+  int* count = d_count + 16 * s_fr_.cset;
+  int* next_counts = d_count + 16 * (s_fr_.cset ^ 1);
   // frame-begin bookkeeping (was a launch of its own): snapshot the cumulative counters, and clear the counter
   // set the NEXT frame will use (the sets alternate, so nothing in this frame touches it)
   if (blockIdx.x == 0 && threadIdx.x < 16)
@@ -101,7 +117,7 @@ __global__ void k_front (Params p, Frame f, Planes P, int cull_blocks, int* __re
     if (i >= n * n * n) return;
     int z = i % n, y = (i / n) % n, x = i / (n * n);
     float cx = center1d (p, p.C, x), cy = center1d (p, p.C, y), cz = center1d (p, p.C, z);
-    if (!frustum_contains (P.pl, cx, cy, cz) || !owns_cell (p, x, y, z)) return;
+    if (!frustum_contains (s_fr_.pl, cx, cy, cz) || !owns_cell (p, x, y, z)) return;
     int k = atomicAdd (count, 1);
     list[k] = i;
     if (q0)
@@ -367,6 +383,7 @@ struct b200tsdf
   int* d_culled = nullptr; int* d_count = nullptr; unsigned long long* d_stats = nullptr;
   size_t culled_cap = 0;
   bool timed = false;
+  bool time_frames = true;       // per-frame event records (ev_t0/ev_t1 and the ring around the dominant kernel)
   bool is_empty = true;          // TSDFVolumeOctree::is_empty_ (cpp:205, hpp:101)
   // fast-path work queues (levels C .. L-3)
   Queues Q{}; int q_levels = 0; QNode* q_mem = nullptr; size_t q_mem_cap = 0;
@@ -374,6 +391,10 @@ struct b200tsdf
   // fused per-cell upper sweeps (coarse cells are the top-tier roots and the block roots are <= 3 levels below)
   bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0; CellTop* d_celltop = nullptr; bool top_path = false;
   bool fast_path = false; int force_general = 0;
+  // device copy of Params (the rare out-of-line paths read it through a pointer) and the ring of per-frame records
+  Params* d_params = nullptr;
+  FrameRec* d_ring = nullptr; FrameRec* h_ring = nullptr; uint64_t ring_seq = 0;
+  cudaEvent_t ev_ring[2] = { nullptr, nullptr };
   // measurement
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
   cudaEvent_t kring[KRING][2] = {};
@@ -461,7 +482,12 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
          && cudaStreamCreateWithFlags (&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess
          && cudaMalloc (&h->d_err, sizeof (int)) == cudaSuccess
          && cudaMalloc (&h->d_count, 64 * sizeof (int)) == cudaSuccess
-         && cudaMalloc (&h->d_stats, ST_TOTAL * sizeof (unsigned long long)) == cudaSuccess;
+         && cudaMalloc (&h->d_stats, ST_TOTAL * sizeof (unsigned long long)) == cudaSuccess
+         && cudaMalloc (&h->d_params, sizeof (Params)) == cudaSuccess
+         && cudaMalloc (&h->d_ring, FRAME_RING * sizeof (FrameRec)) == cudaSuccess
+         && cudaHostAlloc (&h->h_ring, FRAME_RING * sizeof (FrameRec), cudaHostAllocDefault) == cudaSuccess
+         && cudaEventCreateWithFlags (&h->ev_ring[0], cudaEventDisableTiming) == cudaSuccess
+         && cudaEventCreateWithFlags (&h->ev_ring[1], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i)
     ok = cudaEventCreateWithFlags (&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess
       && cudaEventCreateWithFlags (&h->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
@@ -487,6 +513,8 @@ void b200tsdf_destroy (b200tsdf_t* h)
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
   free_volume (h);
   cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled); cudaFree (h->d_scratch);
+  cudaFree (h->d_params); cudaFree (h->d_ring); if (h->h_ring) cudaFreeHost (h->h_ring);
+  for (int i = 0; i < 2; ++i) if (h->ev_ring[i]) cudaEventDestroy (h->ev_ring[i]);
   cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
@@ -614,6 +642,8 @@ int b200tsdf_reset (b200tsdf_t* h)
     p.root_dw = st.root_dw; p.root_split = st.root_split; p.root_rgb = st.root_rgb; p.root_M = st.root_M; p.root_ns = st.root_ns;
   }
   p.err = h->d_err;
+  CK (cudaMemcpyAsync (h->d_params, &p, sizeof (Params), cudaMemcpyHostToDevice, h->stream));
+  CK (cudaStreamSynchronize (h->stream));                            // (&p is host memory that may change after reset)
   // fresh state everywhere (OctreeNode ctor: d=-1, w=0; octree.h:71-74)
   cudaStream_t s = h->stream;
   CK (cudaMemsetAsync (p.keys, 0, pool * sizeof (uint64_t), s));
@@ -641,30 +671,39 @@ int b200tsdf_reset (b200tsdf_t* h)
 }
 
 // ---- integrateCloud (hpp:48-103) ------------------------------------------------------------------
-static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t stride, int xyz_off, int rgba_off, int W, int H, const double* pose)
+// The frame's parameters (pose, planes, cloud pointer, counter set) are written into a FrameRec; the hot kernels
+// read it from the device ring, so the very same launches can be captured once into a CUDA graph and replayed.
+static void fill_rec (b200tsdf* h, FrameRec& r, const unsigned char* d_pts, size_t stride, int xyz_off, int rgba_off, int W, int H, const double* pose)
 {
   const Params& p = h->p;
-  Frame f;
-  fill_frame (h, f, d_pts, stride, xyz_off, rgba_off, W, H, pose);
-  Planes P;
-  b2host::frustum_planes (pose, p.width, p.height, p.fx, p.fy, p.min_sensor, p.max_sensor, P.pl);
-  cudaStream_t s = h->stream;
-  CK (cudaEventRecord (h->ev_t0, s));
-  // counter sets alternate between frames: this frame uses `cnt`, k_front clears the other one for the next frame
-  h->count_set ^= 1;
-  int* cnt = h->d_count + 16 * h->count_set;
-  int* cnt_next = h->d_count + 16 * (h->count_set ^ 1);
+  fill_frame (h, r.f, d_pts, stride, xyz_off, rgba_off, W, H, pose);
+  b2host::frustum_planes (pose, p.width, p.height, p.fx, p.fy, p.min_sensor, p.max_sensor, r.pl);
+  h->count_set ^= 1;                                                  // counter sets alternate between frames
+  r.cset = h->count_set;
+  r.pad_[0] = r.pad_[1] = r.pad_[2] = 0;
+}
+
+// the launches of one frame.  `rec` is the host image of *d_rec (only the paths that are not replayable read it).
+// with_events: bracket the dominant kernel with an event pair of the ring (never inside a capture)
+static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const FrameRec* d_rec, bool with_events)
+{
+  const Params& p = h->p;
+  const Frame& f = rec.f;
+  int* cnt = h->d_count + 16 * rec.cset;
   h->Q.n = cnt;
-  int npix = W * H;
-  int ncells = 1 << (3 * p.C);
+  const int npix = f.width * f.height;
+  const int ncells = 1 << (3 * p.C);
   {
     const int cull_blocks = (ncells + 255) / 256;
-    k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, f, P, cull_blocks, h->d_culled, cnt, h->fast_path ? h->Q.q[0] : nullptr, h->d_stats, cnt_next);
+    k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, d_rec, cull_blocks, h->d_culled, h->d_count, h->fast_path ? h->Q.q[0] : nullptr, h->d_stats);
   }
   h->launches += 1;
-  // dominant kernel, bracketed by a ring of event pairs so bench.py can average its launch duration
-  if (h->kring_pending >= KRING) h->drain_kring (KRING / 2);
-  int kr = h->kring_head;
+  int kr = -1;
+  if (with_events)
+  {
+    if (h->kring_pending >= KRING) h->drain_kring (KRING / 2);
+    kr = h->kring_head;
+  }
   if (h->fast_path)
   {
     const int nl = h->q_levels;
@@ -678,8 +717,8 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
       bli = NL;
       if (h->top_path)
       {
-        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
-        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, h->d_stats);
+        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, h->d_stats);
       }
       else if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
@@ -688,20 +727,20 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
     }
     else
       for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
-    CK (cudaEventRecord (h->kring[kr][0], s));
-    int* bail_list = h->cell_path ? nullptr : h->d_bail;       // the per-cell bottom-up sweeps redo deferred block roots themselves
-    if (p.color) k_blocks<true><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, cnt + 11, h->d_stats);
-    else k_blocks<false><<<h->sm_count * B2_BLK_MINB, BLK_WARPS * 32, 0, s>>> (p, f, Qb, bli, h->d_blist, d_bcount, bail_list, d_bailcount, cnt + 11, h->d_stats);
-    CK (cudaEventRecord (h->kring[kr][1], s));
+    if (kr >= 0) CK (cudaEventRecord (h->kring[kr][0], s));
+    // the dominant kernel: one warp per interior block root, the brick updated in place
+    (void) d_bailcount;
+    if (p.color) k_bricks<true><<<h->sm_count * B2_BD_MINB, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+    else k_bricks<false><<<h->sm_count * B2_BD_MINB, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+    if (kr >= 0) CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
-    if (!h->cell_path) { k_bail<<<8, 64, 0, s>>> (p, f, Qb, bli, h->d_bail, d_bailcount, h->d_stats); h->launches++; }
     if (h->cell_path)
     {
       const int NL = h->cell_nl;
       if (h->top_path)
       {
-        if (p.color) k_celltop_up<true><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
-        else k_celltop_up<false><<<h->sm_count, 128, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        if (p.color) k_celltop_up<true><<<h->sm_count, 128, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        else k_celltop_up<false><<<h->sm_count, 128, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
       }
       else if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
       else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
@@ -713,17 +752,48 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   }
   else
   {
-    CK (cudaEventRecord (h->kring[kr][0], s));
+    if (kr >= 0) CK (cudaEventRecord (h->kring[kr][0], s));
     // general path: every culled cell depth-first (grid covers the worst case; threads past *count exit)
     k_update_dfs<<<(ncells + 31) / 32, 32, 0, s>>> (p, f, h->d_culled, cnt, h->d_stats);
-    CK (cudaEventRecord (h->kring[kr][1], s));
+    if (kr >= 0) CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
   }
-  h->kring_head = (kr + 1) % KRING; h->kring_pending++;
+  if (kr >= 0) { h->kring_head = (kr + 1) % KRING; h->kring_pending++; }
   h->prof_frames++;
-  CK (cudaEventRecord (h->ev_t1, s));
+  return B200TSDF_OK;
+}
+
+// a slot of the record ring for the next frame: the host image is only rewritten once the copy that read it FRAME_RING
+// frames ago has certainly executed
+static int ring_slot (b200tsdf* h, int& slot)
+{
+  slot = (int) (h->ring_seq % FRAME_RING);
+  const int half = FRAME_RING / 2;
+  if (h->ring_seq >= (uint64_t) FRAME_RING && slot % half == 0) CK (cudaEventSynchronize (h->ev_ring[slot / half]));
+  return B200TSDF_OK;
+}
+static int ring_advance (b200tsdf* h, int slot, cudaStream_t s)
+{
+  const int half = FRAME_RING / 2;
+  if (slot % half == half - 1) CK (cudaEventRecord (h->ev_ring[slot / half], s));   // covers the copies of this half
+  h->ring_seq++;
+  return B200TSDF_OK;
+}
+
+static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t stride, int xyz_off, int rgba_off, int W, int H, const double* pose)
+{
+  cudaStream_t s = h->stream;
+  int slot = 0;
+  { int rc = ring_slot (h, slot); if (rc) return rc; }
+  FrameRec& rec = h->h_ring[slot];
+  fill_rec (h, rec, d_pts, stride, xyz_off, rgba_off, W, H, pose);
+  if (h->time_frames) CK (cudaEventRecord (h->ev_t0, s));
+  CK (cudaMemcpyAsync (h->d_ring + slot, &rec, sizeof (FrameRec), cudaMemcpyHostToDevice, s));
+  { int rc = launch_frame (h, s, rec, h->d_ring + slot, h->time_frames); if (rc) return rc; }
+  if (h->time_frames) CK (cudaEventRecord (h->ev_t1, s));
+  { int rc = ring_advance (h, slot, s); if (rc) return rc; }
   CK (cudaGetLastError ());
-  h->timed = true;
+  h->timed = h->time_frames;
   h->is_empty = false;                                             // hpp:101
   return B200TSDF_OK;
 }

@@ -47,6 +47,17 @@ inline const char* derive_params (const b200tsdf_config& c, Params& p, size_t& p
   p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy; p.width = c.image_width; p.height = c.image_height;
   p.fx_f = (float) c.fx; p.fy_f = (float) c.fy; p.cx_f = (float) c.cx; p.cy_f = (float) c.cy;
   p.fast_proj = (c.image_width < 8192 && c.image_height < 8192 && std::fabs (c.cx) < 1e4 && std::fabs (c.cy) < 1e4) ? 1 : 0;
+  {
+    auto at_least = [] (double t) { float f = (float) t; if ((double) f < t) f = std::nextafterf (f, INFINITY); return f; };
+    p.rc_lo_f = at_least (-0.99); p.rc_hi_f = at_least (p.rc_thresh);
+    // error of the float pixel estimate a = x*fx*rcp(z) + cx against the reference's double expression: the product
+    // and the approximate reciprocal contribute < 2^-22 |x fx / z|, the final rounding 2^-24 |a| (brick_direct.cuh)
+    const double M = std::max (c.image_width, c.image_height) + 2.0, cc = std::max (std::fabs (c.cx), std::fabs (c.cy));
+    p.proj_guard = (float) (1.5 * ((M + cc) * std::ldexp (1.0, -22) + M * std::ldexp (1.0, -24)));
+    if (!(p.proj_guard < 0.05f)) p.fast_proj = 0;
+    p.exact_div_ok = (c.max_dist_neg >= 1e-6f && c.max_dist_neg <= 1e6f && std::fabs (c.max_dist_pos) <= 1e6f
+                      && c.max_weight >= 0.f && c.max_weight <= 1e9f && c.min_sensor_dist >= 1e-6f && c.max_sensor_dist <= 1e6f) ? 1 : 0;
+  }
   p.color = c.integrate_color != 0; p.track_var = c.track_variance != 0;
   p.shard_rank = c.shard_rank; p.shard_count = c.shard_count;
   p.pool_mask = (uint32_t) (pool - 1);

@@ -134,6 +134,11 @@ struct Params
   double fx, fy, cx, cy;
   float fx_f, fy_f, cx_f, cy_f;   // float-rounded intrinsics for the guarded fast projection (see project_pixel)
   int fast_proj;                  // 1 when the guard's error bound holds (image < 8192 px)
+  // float forms of the double comparisons, used by the brick kernel (brick_direct.cuh): for a float d,
+  // (double) d < t  <=>  d < (smallest float >= t)
+  float rc_lo_f, rc_hi_f;         // thresholds -0.99 and rc_thresh of the return code (hpp:209-214)
+  float proj_guard;               // half-width of the band around an integer inside which the float pixel estimate is not trusted
+  int exact_div_ok;               // 1 when every divisor of the update lies where __fdiv_rn takes its fast path (see div_with)
   int width, height;
   int color, track_var;
   // sharding: this device owns coarse cells with cell_hash % shard_count == shard_rank
