@@ -4,7 +4,8 @@
 A "step" is one pass of the hot path over one batch of FRAMES_PER_STEP synthetic 640x480 depth
 frames (ICL-NUIM-shaped interior stream S2, colour on, 2048^3 / 10 m grid: BASELINE.json
 configs[2]).  The JSON line carries
-  value        frames/s with the clouds already resident in HBM (b200tsdf_integrate_device),
+  value        frames/s with the clouds already resident in HBM (b200tsdf_integrate_batch_device: one
+               CUDA-graph launch per step of 32 frames),
   e2e          frames/s through the public API from pinned HOST buffers (H2D inside the timed
                region, a D2H read of the per-step result),
   roofline     achieved algorithmic GB/s of the dominant kernel against the measured HBM peak,
@@ -39,12 +40,32 @@ W, H = CAM.width, CAM.height
 
 
 def make_inputs(n=N_DISTINCT, color=True):
+    """The first n frames of THE bench stream (both arms cycle through the same N_DISTINCT poses / clouds)."""
     poses, clouds = [], []
     for f in range(n):
-        pose = synth.orbit_pose(SCENE, f * (100 // n if n <= 100 else 1), 100)
+        pose = synth.orbit_pose(SCENE, f * (100 // N_DISTINCT), 100)
         poses.append(pose)
         clouds.append(synth.make_frame(SCENE, pose, CAM, color=color, noise_seed=12345, frame=f))
     return poses, clouds
+
+
+class HostLoad:
+    """Busy-loops on every host core (stand-in for `stress-ng --cpu $(nproc)`, which this image lacks)."""
+
+    def __init__(self, n):
+        self.n, self.procs = n, []
+
+    def __enter__(self):
+        for _ in range(self.n):
+            self.procs.append(subprocess.Popen([sys.executable, "-c", "while True: pass"]))
+        time.sleep(0.5)
+        return self
+
+    def __exit__(self, *a):
+        for p in self.procs:
+            p.kill()
+        for p in self.procs:
+            p.wait()
 
 
 def measured_peaks():
@@ -136,9 +157,11 @@ def cpu_arm(poses, clouds, nframes, threads_list, kind=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    poses, clouds = make_inputs(16)
-    nproc = os.cpu_count() or 1
     frames_per_step = 4
+    n_need = min(N_DISTINCT, 3 + (args.warmup + args.steps) * frames_per_step)
+    poses, clouds = make_inputs(n_need)
+    ND = len(clouds)
+    nproc = os.cpu_count() or 1
     from oracle import oracle_py
     kind = "reference" if os.path.exists(oracle_py.REF_LIB) else "port"
     import ctypes
@@ -172,11 +195,11 @@ def run_reference(args, rank, world):
     k = 0
     for _ in range(args.warmup):
         for _ in range(frames_per_step):
-            v.integrate(clouds[k % 16], poses[k % 16]); k += 1
+            v.integrate(clouds[k % ND], poses[k % ND]); k += 1
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for _ in range(frames_per_step):
-            v.integrate(clouds[k % 16], poses[k % 16]); k += 1
+            v.integrate(clouds[k % ND], poses[k % ND]); k += 1
     dt = time.perf_counter() - t0
     fps = args.steps * frames_per_step / dt
     line = {
@@ -207,6 +230,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-load", action="store_true", help="skip the leg that repeats the device-resident measurement with all host cores busy")
     ap.add_argument("--pool-log2", type=int, default=18, help="brick pool capacity = 2^N slots (the bench scene allocates ~37k bricks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -247,10 +271,18 @@ def main():
     torch.cuda.synchronize()
     stride = 32
 
+    d_ptrs = [t.data_ptr() for t in d_clouds]
+
     def step_device(k0):
+        # one step = FRAMES_PER_STEP consecutive integrateCloud calls submitted as ONE batch: one record upload + one CUDA-graph launch
+        idx = [(k0 + j) % N_DISTINCT for j in range(FRAMES_PER_STEP)]
+        vol.integrateBatchDevice([d_ptrs[i] for i in idx], H, W, stride, [poses[i] for i in idx], rgba_off=16)
+
+    def step_device_frames(k0):
+        # the same frames one integrateCloud call (4 kernel launches) at a time: the path whose dominant kernel CUDA events can bracket
         for j in range(FRAMES_PER_STEP):
             i = (k0 + j) % N_DISTINCT
-            vol.integrateCloudDevice(d_clouds[i].data_ptr(), H, W, stride, poses[i], rgba_off=16)
+            vol.integrateCloudDevice(d_ptrs[i], H, W, stride, poses[i], rgba_off=16)
 
     def step_host(k0):
         for j in range(FRAMES_PER_STEP):
@@ -259,7 +291,20 @@ def main():
             vol.integrateCloudAsync(h.data_ptr(), H, W, stride, poses[i], rgba_off=16)   # pinned buffer stays alive
         return vol.stats().n_updates         # D2H read of the step's result (synchronizes)
 
-    # ---- device-resident leg ---------------------------------------------------------------
+    def timed(step_fn, steps):
+        nonlocal k
+        barrier()
+        vol.profile_begin()
+        for _ in range(steps):
+            step_fn(k); k += FRAMES_PER_STEP
+        prof = vol.profile_end()
+        barrier()
+        ms = torch.tensor([prof.ms_elapsed], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return prof, float(ms.item())
+
+    # ---- device-resident leg (headline `value`): batched graph launches ------------------------
     # (nvidia-smi needs ~0.2 s to start: sample from before the warm-up to after the end-to-end leg)
     sampler = ClockSampler(local_rank); sampler.start()
     time.sleep(0.4)
@@ -267,18 +312,25 @@ def main():
     for _ in range(args.warmup):
         step_device(k); k += FRAMES_PER_STEP
     vol.sync()
-    barrier()
-    vol.profile_begin()
-    for _ in range(args.steps):
-        step_device(k); k += FRAMES_PER_STEP
-    prof = vol.profile_end()
-    barrier()
-    ms = torch.tensor([prof.ms_elapsed], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    prof, ms_total = timed(step_device, args.steps)
     nframes = args.steps * FRAMES_PER_STEP
     value = nframes / (ms_total / 1e3)
+
+    # ---- the same work one frame per call, the dominant kernel bracketed by CUDA events (roofline leg) ----
+    for _ in range(2):
+        step_device_frames(k); k += FRAMES_PER_STEP
+    prof_f, ms_frames = timed(step_device_frames, args.steps)
+
+    # ---- the batched leg again with every host core busy (a library must not depend on an idle host) ----
+    host_load = None
+    if not args.no_host_load:
+        import contextlib
+        with (HostLoad(os.cpu_count() or 1) if rank == 0 else contextlib.nullcontext()):
+            step_device(k); k += FRAMES_PER_STEP
+            vol.sync()
+            _, ms_loaded = timed(step_device, max(3, args.steps // 2))
+        host_load = {"value": max(3, args.steps // 2) * FRAMES_PER_STEP / (ms_loaded / 1e3), "unit": "frames/s",
+                     "load": f"{os.cpu_count()} busy-loop processes (one per host core) during the batched device-resident leg"}
 
     # ---- end-to-end leg (host buffers, public API) ---------------------------------------------
     for _ in range(max(1, args.warmup // 2)):
@@ -302,24 +354,41 @@ def main():
     if world > 1:
         dist.all_reduce(upd, op=dist.ReduceOp.SUM)
     peak, peak_src = measured_peaks()
-    # algorithmic bytes per frame: 4 W H (depth) + N_upd * (8 read + 8 write) [+ (4+4) with colour]
-    b_alg_local = 4.0 * W * H * prof.n_frames + prof.n_updates * (16.0 + 8.0)
-    achieved = b_alg_local / (prof.ms_kernel / 1e3) / 1e9 if prof.ms_kernel > 0 else 0.0
+
+    def alg_bytes(pr):
+        # algorithmic bytes: 4 W H (depth) + N_upd * (8 read + 8 write) [+ (4+4) with colour]
+        return 4.0 * W * H * pr.n_frames + pr.n_updates * (16.0 + 8.0)
+
+    # single-frame figure: CUDA-event pairs around k_bricks on the engine's stream, one frame per call
+    achieved = alg_bytes(prof_f) / (prof_f.ms_kernel / 1e3) / 1e9 if prof_f.ms_kernel > 0 else 0.0
+    # batched figure: the same kernel inside the 32-frame graph launches of the headline leg, timed on the device
+    # (%globaltimer, first block start -> last block end; no event can be placed inside a replayed graph)
+    batched = None
+    if prof.kernel_launches_device > 0 and prof.ms_kernel_device > 0:
+        a_b = alg_bytes(prof) * (prof.kernel_launches_device / max(1, prof.n_frames)) / (prof.ms_kernel_device / 1e3) / 1e9
+        batched = {"frames_per_graph_launch": FRAMES_PER_STEP, "achieved": a_b, "frac": a_b / peak,
+                   "us_per_launch": 1e3 * prof.ms_kernel_device / prof.kernel_launches_device,
+                   "launches_timed": int(prof.kernel_launches_device), "timer": "%globaltimer inside k_bricks"}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if world == 1 and os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    st_last = vol.stats()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "brick update (k_update_*)",
-                "bytes_per_launch": b_alg_local / max(1, prof.kernel_launches),
-                "us_per_launch": 1e3 * prof.ms_kernel / max(1, prof.kernel_launches),
-                "updates_per_frame": prof.n_updates / max(1, prof.n_frames),
-                "blocks_last_frame": int(vol.stats().n_block_visits), "bricks_allocated": int(vol.stats().n_bricks),
-                "general_path_last_frame": {"block_bails": int(vol.stats().n_bail), "upper_slow_folds": int(vol.stats().reserved),
-                                            "upper_slow_visits": int(vol.stats().n_slow_visits)}}
+                "traffic": traffic,
+                "traffic_source": "ncu --set full capture of this kernel on this workload at N=1 (profiles/traffic.json); not measured at N>1",
+                "peak_source": peak_src, "kernel": "k_bricks (one warp per interior 8^3 block, brick updated in place)",
+                "bytes_per_launch": alg_bytes(prof_f) / max(1, prof_f.kernel_launches),
+                "us_per_launch": 1e3 * prof_f.ms_kernel / max(1, prof_f.kernel_launches),
+                "us_per_launch_device_timer": 1e3 * prof_f.ms_kernel_device / max(1, prof_f.kernel_launches_device),
+                "updates_per_frame": prof_f.n_updates / max(1, prof_f.n_frames),
+                "frames_per_s_one_call_per_frame": nframes / (ms_frames / 1e3),
+                "batched": batched,
+                "blocks_last_frame": int(st_last.n_block_visits), "bricks_allocated": int(st_last.n_bricks),
+                "general_path_last_frame": {"upper_slow_folds": int(st_last.reserved), "upper_slow_visits": int(st_last.n_slow_visits)}}
 
     if rank == 0:
         cpu = None
@@ -337,6 +406,8 @@ def main():
                     "h2d_bytes_per_step": int(prof_e.h2d_bytes // args.steps), "d2h_bytes_per_step": int(prof_e.d2h_bytes // args.steps),
                     "timing": "max(CUDA events on the engine stream, host wall clock) over ranks"},
             "gpu_launches": int(prof.total_launches),
+            "graph_launches": int(prof.graph_launches),
+            "host_load_leg": host_load,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "updates_total": float(upd.item()),

@@ -35,8 +35,11 @@ struct FrameRec
   Frame f;
   float pl[6][4];          // frustum planes (host_math.h)
   int cset;                // which of the two per-frame counter sets this frame uses
-  int pad_[3];
+  int timing;              // 1: the brick kernel stamps kt[] with %globaltimer (profiling; works inside a replayed graph)
+  int pad_[2];
+  unsigned long long kt[2];// [0] start of the brick kernel (ns), [1] end of its last block; zeroed by the record upload
 };
+__device__ __forceinline__ unsigned long long global_ns () { unsigned long long t; asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 constexpr int MAX_QLEVELS = 8;
 struct Queues
@@ -255,14 +258,12 @@ __device__ __forceinline__ int upper_visit (const Params& p, const Frame& f, int
 }
 
 // fold the children's return codes into an interior node (hpp:131-142 / :176-188 + fall-through)
-__device__ unsigned long long* g_diag;   // [0] slow folds in the upper sweeps, [1] visits inside them (diagnostics)
-__device__ unsigned long long* g_dbg;    // optional phase timing of k_celltop_up (b200tsdf_debug_timing), normally null
 __device__ __noinline__ int upper_fold_slow (const Params& p, const Frame& f, const NodePos& n, unsigned long long& upd, unsigned long long& vis)
 {
   Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
   int rc = update_voxel_dfs (p, f, n, cnt);
   upd += cnt.n_updates; vis += cnt.n_visits - 1;
-  if (g_diag) { atomicAdd (&g_diag[0], 1ull); atomicAdd (&g_diag[1], (unsigned long long) cnt.n_visits); }
+  if (p.diag) { atomicAdd (&p.diag[0], 1ull); atomicAdd (&p.diag[1], (unsigned long long) cnt.n_visits); }
   return rc;
 }
 // leaf visit (hpp:143-218) of a node whose pre-existing children were just pruned, by one WARP: if the node
@@ -1177,6 +1178,8 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
   unsigned long long upd = 0, vis = 0;
   int count = d_count[16 * fr->cset];
   if (count > cell_cap) count = cell_cap;
+  if (fr->timing && blockIdx.x == 0 && threadIdx.x == 0 && fr->kt[1] > fr->kt[0])
+  { atomicAdd (&stats[5], fr->kt[1] - fr->kt[0]); atomicAdd (&stats[6], 1ull); }          // device-timed brick kernel of this frame
   const float sizeC = level_size (p, p.C);
   const float off1 = sizeC * 0.25f;
   constexpr int STRIDE = 585;
@@ -1301,19 +1304,19 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
       if (top->kind[0] == KIND_NEW) { if (lane == 0) top_fallthrough_new (p, f, nc, top->dnew[0], top->uv[0], upd); }
       else { __threadfence_block (); leaf_visit_warp_bfs (p, f, nc, s_rec[threadIdx.x >> 5], &s_cnt[threadIdx.x >> 5], upd, vis); }
     }
-    if (g_dbg && lane == 0)
+    if (p.dbg && lane == 0)
     {
       const long long cD = clock64 ();
       const unsigned long long tag = ((unsigned long long) (dbg_slow2 & 0xFF) << 24) | ((unsigned long long) (dbg_slow1 & 0xF) << 20) | ((unsigned long long) (dbg_cell & 3) << 18) | (unsigned long long) (ci & 0x3FFFF);
-      atomicMax (&g_dbg[0], ((unsigned long long) (cD - tc0) << 32) | tag);
-      atomicMax (&g_dbg[1], ((unsigned long long) (cA - tc0) << 32) | tag);
-      atomicMax (&g_dbg[2], ((unsigned long long) (cB - cA) << 32) | tag);
-      atomicMax (&g_dbg[3], ((unsigned long long) (cC - cB) << 32) | tag);
-      atomicMax (&g_dbg[4], ((unsigned long long) (cD - cC) << 32) | tag);
-      atomicMax (&g_dbg[5], ((unsigned long long) (tc0 - c_entry) << 32) | tag);
-      atomicAdd (&g_dbg[6], (unsigned long long) dbg_slow2); atomicAdd (&g_dbg[7], (unsigned long long) dbg_slow1);
-      atomicAdd (&g_dbg[8], (unsigned long long) (dbg_cell == 2)); atomicAdd (&g_dbg[9], (unsigned long long) (dbg_cell == 1));
-      atomicAdd (&g_dbg[10], 1ull);
+      atomicMax (&p.dbg[0], ((unsigned long long) (cD - tc0) << 32) | tag);
+      atomicMax (&p.dbg[1], ((unsigned long long) (cA - tc0) << 32) | tag);
+      atomicMax (&p.dbg[2], ((unsigned long long) (cB - cA) << 32) | tag);
+      atomicMax (&p.dbg[3], ((unsigned long long) (cC - cB) << 32) | tag);
+      atomicMax (&p.dbg[4], ((unsigned long long) (cD - cC) << 32) | tag);
+      atomicMax (&p.dbg[5], ((unsigned long long) (tc0 - c_entry) << 32) | tag);
+      atomicAdd (&p.dbg[6], (unsigned long long) dbg_slow2); atomicAdd (&p.dbg[7], (unsigned long long) dbg_slow1);
+      atomicAdd (&p.dbg[8], (unsigned long long) (dbg_cell == 2)); atomicAdd (&p.dbg[9], (unsigned long long) (dbg_cell == 1));
+      atomicAdd (&p.dbg[10], 1ull);
     }
   }
   __syncwarp ();

@@ -383,7 +383,7 @@ struct b200tsdf
   int* d_culled = nullptr; int* d_count = nullptr; unsigned long long* d_stats = nullptr;
   size_t culled_cap = 0;
   bool timed = false;
-  bool time_frames = true;       // per-frame event records (ev_t0/ev_t1 and the ring around the dominant kernel)
+  bool time_frames = false;      // set between profile_begin / profile_end: per-frame event records (ev_t0/ev_t1 and the ring around the dominant kernel)
   bool is_empty = true;          // TSDFVolumeOctree::is_empty_ (cpp:205, hpp:101)
   // fast-path work queues (levels C .. L-3)
   Queues Q{}; int q_levels = 0; QNode* q_mem = nullptr; size_t q_mem_cap = 0;
@@ -391,10 +391,19 @@ struct b200tsdf
   // fused per-cell upper sweeps (coarse cells are the top-tier roots and the block roots are <= 3 levels below)
   bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0; CellTop* d_celltop = nullptr; bool top_path = false;
   bool fast_path = false; int force_general = 0;
+  int bd_minb = 8;               // resident CTAs per SM the brick kernel is compiled for (tuning knob: B200TSDF_BD_MINB=6|8)
   // device copy of Params (the rare out-of-line paths read it through a pointer) and the ring of per-frame records
   Params* d_params = nullptr;
+  unsigned long long* d_dbg = nullptr;     // phase-timing counters of k_celltop_up once b200tsdf_debug_timing armed them
+  int* h_err = nullptr;                    // pinned image of the device error bits, refreshed behind every frame (see note_device_err)
   FrameRec* d_ring = nullptr; FrameRec* h_ring = nullptr; uint64_t ring_seq = 0;
   cudaEvent_t ev_ring[2] = { nullptr, nullptr };
+  // batches (b200tsdf_integrate_batch_device): their own record ring, used half by half, and one captured graph per
+  // (half, batch size); a graph is valid until the next reset()
+  FrameRec* d_bring = nullptr; FrameRec* h_bring = nullptr; int bring_half = 0; bool bring_used[2] = { false, false };
+  cudaEvent_t ev_bring[2] = { nullptr, nullptr };
+  cudaGraphExec_t batch_exec[2][FRAME_RING / 2 + 1] = {};
+  int launches_per_frame = 0; long long graph_launches = 0, prof_graph0 = 0;
   // measurement
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
   cudaEvent_t kring[KRING][2] = {};
@@ -441,6 +450,13 @@ void free_volume (b200tsdf* h)
   h->pool = 0; h->root_n = 0;
 }
 
+void drop_batch_graphs (b200tsdf* h)
+{
+  for (int a = 0; a < 2; ++a)
+    for (int n = 0; n <= FRAME_RING / 2; ++n)
+      if (h->batch_exec[a][n]) { cudaGraphExecDestroy (h->batch_exec[a][n]); h->batch_exec[a][n] = nullptr; }
+}
+
 int check_device_err (b200tsdf* h)
 {
   int e = 0;
@@ -451,6 +467,20 @@ int check_device_err (b200tsdf* h)
   if (e & ERR_QUEUE_FULL) return h->fail (B200TSDF_ENOMEM, "internal: work queue overflow");
   return 0;
 }
+
+// Deferred error reporting for the calls that do not wait for their kernels: a 4-byte copy of the (sticky) device error bits
+// into pinned memory is queued behind the work, and every entry point looks at the pinned word first.  An overflow
+// (pool, queue) or an inconsistency is therefore reported by the call that follows the frame which hit it, at the latest
+// by b200tsdf_sync / get_stats / mesh / save, instead of being served silently.
+int pending_device_err (b200tsdf* h)
+{
+  const int e = *(volatile int*) h->h_err;
+  if (!e) return 0;
+  if (e & ERR_POOL_FULL) return h->fail (B200TSDF_ENOMEM, "brick pool exhausted in an earlier frame (raise pool_log2); the volume is incomplete");
+  if (e & ERR_MISSING_BRICK) return h->fail (B200TSDF_ESTATE, "internal: split node without brick (earlier frame)");
+  return h->fail (B200TSDF_ENOMEM, "internal: work queue overflow in an earlier frame; the volume is incomplete");
+}
+void note_device_err (b200tsdf* h, cudaStream_t s) { cudaMemcpyAsync (h->h_err, h->d_err, sizeof (int), cudaMemcpyDeviceToHost, s); }
 
 void fill_frame (const b200tsdf* h, Frame& f, const unsigned char* d_pts, size_t stride, int xyz_off, int rgba_off, int W, int H, const double* pose)
 {
@@ -475,6 +505,7 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   b200tsdf* h = new b200tsdf;
   if (cfg) h->cfg_pending = *cfg; else b200tsdf_default_config (&h->cfg_pending);
   h->device = h->cfg_pending.device;
+  if (const char* e = std::getenv ("B200TSDF_BD_MINB")) { if (std::atoi (e) == 6) h->bd_minb = 6; }
   if (h->device < 0 || h->device >= ndev) { delete h; return B200TSDF_EINVAL; }
   bool ok = cudaSetDevice (h->device) == cudaSuccess
          && cudaDeviceGetAttribute (&h->sm_count, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess
@@ -484,10 +515,15 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
          && cudaMalloc (&h->d_count, 64 * sizeof (int)) == cudaSuccess
          && cudaMalloc (&h->d_stats, ST_TOTAL * sizeof (unsigned long long)) == cudaSuccess
          && cudaMalloc (&h->d_params, sizeof (Params)) == cudaSuccess
+         && cudaHostAlloc (&h->h_err, sizeof (int), cudaHostAllocDefault) == cudaSuccess
          && cudaMalloc (&h->d_ring, FRAME_RING * sizeof (FrameRec)) == cudaSuccess
          && cudaHostAlloc (&h->h_ring, FRAME_RING * sizeof (FrameRec), cudaHostAllocDefault) == cudaSuccess
          && cudaEventCreateWithFlags (&h->ev_ring[0], cudaEventDisableTiming) == cudaSuccess
-         && cudaEventCreateWithFlags (&h->ev_ring[1], cudaEventDisableTiming) == cudaSuccess;
+         && cudaEventCreateWithFlags (&h->ev_ring[1], cudaEventDisableTiming) == cudaSuccess
+         && cudaMalloc (&h->d_bring, FRAME_RING * sizeof (FrameRec)) == cudaSuccess
+         && cudaHostAlloc (&h->h_bring, FRAME_RING * sizeof (FrameRec), cudaHostAllocDefault) == cudaSuccess
+         && cudaEventCreateWithFlags (&h->ev_bring[0], cudaEventDisableTiming) == cudaSuccess
+         && cudaEventCreateWithFlags (&h->ev_bring[1], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i)
     ok = cudaEventCreateWithFlags (&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess
       && cudaEventCreateWithFlags (&h->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
@@ -496,8 +532,8 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
           && cudaEventCreate (&h->ev_p0) == cudaSuccess && cudaEventCreate (&h->ev_p1) == cudaSuccess;
   for (int i = 0; ok && i < KRING; ++i)
     ok = cudaEventCreate (&h->kring[i][0]) == cudaSuccess && cudaEventCreate (&h->kring[i][1]) == cudaSuccess;
+  if (ok) *h->h_err = 0;
   if (ok) { cudaMemset (h->d_err, 0, sizeof (int)); cudaMemset (h->d_stats, 0, ST_TOTAL * sizeof (unsigned long long)); }
-  if (ok) { unsigned long long* dp = h->d_stats + 3; ok = cudaMemcpyToSymbol (g_diag, &dp, sizeof (dp)) == cudaSuccess; }
   // the depth-first general path recurses up to (L - C + 1) levels
   if (ok) cudaDeviceSetLimit (cudaLimitStackSize, 16384);
   if (!ok) { b200tsdf_destroy (h); return B200TSDF_ECUDA; }
@@ -513,8 +549,12 @@ void b200tsdf_destroy (b200tsdf_t* h)
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
   free_volume (h);
   cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled); cudaFree (h->d_scratch);
+  cudaFree (h->d_dbg); if (h->h_err) cudaFreeHost (h->h_err);
   cudaFree (h->d_params); cudaFree (h->d_ring); if (h->h_ring) cudaFreeHost (h->h_ring);
   for (int i = 0; i < 2; ++i) if (h->ev_ring[i]) cudaEventDestroy (h->ev_ring[i]);
+  drop_batch_graphs (h);
+  cudaFree (h->d_bring); if (h->h_bring) cudaFreeHost (h->h_bring);
+  for (int i = 0; i < 2; ++i) if (h->ev_bring[i]) cudaEventDestroy (h->ev_bring[i]);
   cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
@@ -559,8 +599,11 @@ int b200tsdf_reset (b200tsdf_t* h)
 
   CK (cudaStreamSynchronize (h->stream));
   CK (cudaStreamSynchronize (h->copy_stream));
+  drop_batch_graphs (h);                                   // captured launches carry the old configuration
+  h->bring_used[0] = h->bring_used[1] = false;
   if (pool != h->pool || root_n != h->root_n || color != h->alloc_color || var != h->alloc_var)
   {
+    h->has_volume = false;                                 // a failed allocation below must not leave a half-built volume usable
     free_volume (h);
     CK (cudaMalloc (&h->p.keys, pool * sizeof (uint64_t)));
     CK (cudaMalloc (&h->p.nodes, pool * BRICK_NODES * sizeof (float2)));
@@ -642,6 +685,8 @@ int b200tsdf_reset (b200tsdf_t* h)
     p.root_dw = st.root_dw; p.root_split = st.root_split; p.root_rgb = st.root_rgb; p.root_M = st.root_M; p.root_ns = st.root_ns;
   }
   p.err = h->d_err;
+  p.diag = h->d_stats + 3;
+  p.dbg = h->d_dbg;
   CK (cudaMemcpyAsync (h->d_params, &p, sizeof (Params), cudaMemcpyHostToDevice, h->stream));
   CK (cudaStreamSynchronize (h->stream));                            // (&p is host memory that may change after reset)
   // fresh state everywhere (OctreeNode ctor: d=-1, w=0; octree.h:71-74)
@@ -656,6 +701,7 @@ int b200tsdf_reset (b200tsdf_t* h)
   if (color) CK (cudaMemsetAsync (p.root_rgb, 0, root_n * sizeof (uchar4), s));
   if (var) { CK (cudaMemsetAsync (p.root_M, 0, root_n * sizeof (float), s)); CK (cudaMemsetAsync (p.root_ns, 0, root_n * sizeof (int), s)); }
   CK (cudaMemsetAsync (h->d_err, 0, sizeof (int), s));
+  *h->h_err = 0;
   CK (cudaMemsetAsync (h->d_count, 0, 64 * sizeof (int), s));
   h->count_set = 0;
   CK (cudaMemsetAsync (h->d_stats, 0, ST_TOTAL * sizeof (unsigned long long), s));
@@ -680,7 +726,8 @@ static void fill_rec (b200tsdf* h, FrameRec& r, const unsigned char* d_pts, size
   b2host::frustum_planes (pose, p.width, p.height, p.fx, p.fy, p.min_sensor, p.max_sensor, r.pl);
   h->count_set ^= 1;                                                  // counter sets alternate between frames
   r.cset = h->count_set;
-  r.pad_[0] = r.pad_[1] = r.pad_[2] = 0;
+  r.timing = h->time_frames ? 1 : 0;
+  r.pad_[0] = r.pad_[1] = 0; r.kt[0] = r.kt[1] = 0;
 }
 
 // the launches of one frame.  `rec` is the host image of *d_rec (only the paths that are not replayable read it).
@@ -730,8 +777,16 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][0], s));
     // the dominant kernel: one warp per interior block root, the brick updated in place
     (void) d_bailcount;
-    if (p.color) k_bricks<true><<<h->sm_count * B2_BD_MINB, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
-    else k_bricks<false><<<h->sm_count * B2_BD_MINB, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+    if (h->bd_minb == 6)
+    {
+      if (p.color) k_bricks<true, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+      else k_bricks<false, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+    }
+    else
+    {
+      if (p.color) k_bricks<true, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+      else k_bricks<false, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+    }
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
     if (h->cell_path)
@@ -783,6 +838,7 @@ static int ring_advance (b200tsdf* h, int slot, cudaStream_t s)
 static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t stride, int xyz_off, int rgba_off, int W, int H, const double* pose)
 {
   cudaStream_t s = h->stream;
+  if (int rc = pending_device_err (h)) return rc;
   int slot = 0;
   { int rc = ring_slot (h, slot); if (rc) return rc; }
   FrameRec& rec = h->h_ring[slot];
@@ -791,10 +847,24 @@ static int integrate_on_device (b200tsdf* h, const unsigned char* d_pts, size_t 
   CK (cudaMemcpyAsync (h->d_ring + slot, &rec, sizeof (FrameRec), cudaMemcpyHostToDevice, s));
   { int rc = launch_frame (h, s, rec, h->d_ring + slot, h->time_frames); if (rc) return rc; }
   if (h->time_frames) CK (cudaEventRecord (h->ev_t1, s));
+  note_device_err (h, s);
   { int rc = ring_advance (h, slot, s); if (rc) return rc; }
   CK (cudaGetLastError ());
   h->timed = h->time_frames;
   h->is_empty = false;                                             // hpp:101
+  return B200TSDF_OK;
+}
+
+// layout of an organized cloud as the integrate entry points accept it (the same checks everywhere)
+static int check_cloud_layout (b200tsdf* h, size_t stride, int xyz_off, int rgba_off, int width, int height)
+{
+  if (width <= 0 || height <= 0) return h->fail (B200TSDF_EINVAL, "bad cloud shape");
+  if (stride < 12 || (stride & 3) || xyz_off < 0 || (xyz_off & 3) || (size_t) xyz_off + 12 > stride
+      || (rgba_off >= 0 && ((size_t) rgba_off + 4 > stride || (rgba_off & 3))))
+    return h->fail (B200TSDF_EINVAL, "bad point layout (need 4-byte aligned xyz_off + 12 <= stride and rgba_off + 4 <= stride)");
+  if ((double) width * (double) height * (double) stride >= 2147483648.0) return h->fail (B200TSDF_EINVAL, "organized cloud of 2 GiB or more");
+  if (width != h->cfg.image_width || height != h->cfg.image_height)
+    return h->fail (B200TSDF_EINVAL, "organized cloud size differs from setImageSize() (the reference indexes cloud(u,v) with the image size, cpp:611-617)");
   return B200TSDF_OK;
 }
 
@@ -803,11 +873,71 @@ int b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t strid
 {
   if (!h || !d_points || !pose) return B200TSDF_EINVAL;
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
-  if (width <= 0 || height <= 0 || stride < 12) return h->fail (B200TSDF_EINVAL, "bad cloud shape");
-  if (width != h->cfg.image_width || height != h->cfg.image_height)
-    return h->fail (B200TSDF_EINVAL, "organized cloud size differs from setImageSize()");
+  if (int rc = check_cloud_layout (h, stride, xyz_off, rgba_off, width, height)) return rc;
   cudaSetDevice (h->device);
   return integrate_on_device (h, (const unsigned char*) d_points, stride, xyz_off, rgba_off, width, height, pose);
+}
+
+// a batch of frames resident in device memory: one upload of the frame records, one graph launch
+int b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_points, size_t stride, int xyz_off, int rgba_off,
+                                     int width, int height, const double* poses_c2w)
+{
+  if (!h || n < 0 || (n && (!d_points || !poses_c2w))) return B200TSDF_EINVAL;
+  if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
+  if (int rc = check_cloud_layout (h, stride, xyz_off, rgba_off, width, height)) return rc;
+  cudaSetDevice (h->device);
+  if (int rc = pending_device_err (h)) return rc;
+  constexpr int HALF = FRAME_RING / 2;
+  cudaStream_t s = h->stream;
+  for (int done = 0; done < n;)
+  {
+    const int m = std::min (HALF, n - done);
+    if (!h->top_path)
+    {
+      // grid shapes whose launches are not replayable: frame by frame
+      for (int i = 0; i < m; ++i)
+        if (int rc = integrate_on_device (h, (const unsigned char*) d_points[done + i], stride, xyz_off, rgba_off, width, height, poses_c2w + 16 * (size_t) (done + i))) return rc;
+      done += m;
+      continue;
+    }
+    const int a = h->bring_half;
+    if (h->bring_used[a]) CK (cudaEventSynchronize (h->ev_bring[a]));      // the copy that last read this half of the host image has run
+    FrameRec* recs = h->h_bring + a * HALF;
+    for (int i = 0; i < m; ++i)
+    {
+      if (!d_points[done + i]) return h->fail (B200TSDF_EINVAL, "null cloud in batch");
+      fill_rec (h, recs[i], (const unsigned char*) d_points[done + i], stride, xyz_off, rgba_off, width, height, poses_c2w + 16 * (size_t) (done + i));
+    }
+    cudaGraphExec_t& exec = h->batch_exec[a][m];          // (nothing of a frame is baked into the launches: they read the record)
+    CK (cudaMemcpyAsync (h->d_bring + a * HALF, recs, (size_t) m * sizeof (FrameRec), cudaMemcpyHostToDevice, s));
+    if (!exec)
+    {
+      const long long l0 = h->launches, f0 = h->prof_frames;
+      cudaGraph_t g = nullptr;
+      CK (cudaStreamBeginCapture (s, cudaStreamCaptureModeThreadLocal));
+      int rc = B200TSDF_OK;
+      for (int i = 0; i < m && rc == B200TSDF_OK; ++i) rc = launch_frame (h, s, recs[i], h->d_bring + a * HALF + i, false);
+      cudaError_t ce = cudaStreamEndCapture (s, &g);
+      h->launches_per_frame = (int) ((h->launches - l0) / std::max (1, m));
+      h->launches = l0; h->prof_frames = f0;
+      if (rc) { if (g) cudaGraphDestroy (g); return rc; }
+      if (ce != cudaSuccess) return h->fail (B200TSDF_ECUDA, std::string ("graph capture: ") + cudaGetErrorString (ce));
+      ce = cudaGraphInstantiate (&exec, g, 0);
+      cudaGraphDestroy (g);
+      if (ce != cudaSuccess) { exec = nullptr; return h->fail (B200TSDF_ECUDA, std::string ("graph instantiate: ") + cudaGetErrorString (ce)); }
+    }
+    CK (cudaGraphLaunch (exec, s));
+    note_device_err (h, s);
+    CK (cudaEventRecord (h->ev_bring[a], s));
+    h->bring_used[a] = true; h->bring_half ^= 1;
+    h->launches += (long long) m * h->launches_per_frame; h->graph_launches++;
+    h->prof_frames += m;
+    done += m;
+  }
+  h->timed = false;
+  if (n) h->is_empty = false;
+  CK (cudaGetLastError ());
+  return B200TSDF_OK;
 }
 
 static int integrate_host (b200tsdf* h, const void* points, size_t stride, int xyz_off, int rgba_off,
@@ -815,9 +945,7 @@ static int integrate_host (b200tsdf* h, const void* points, size_t stride, int x
 {
   if (!h || !points || !pose) return B200TSDF_EINVAL;
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
-  if (width <= 0 || height <= 0 || stride < 12) return h->fail (B200TSDF_EINVAL, "bad cloud shape");
-  if (width != h->cfg.image_width || height != h->cfg.image_height)
-    return h->fail (B200TSDF_EINVAL, "organized cloud size differs from setImageSize() (the reference indexes cloud(u,v) with the image size, cpp:611-617)");
+  if (int rc = check_cloud_layout (h, stride, xyz_off, rgba_off, width, height)) return rc;
   cudaSetDevice (h->device);
   size_t bytes = (size_t) width * height * stride;
   if (bytes > h->frame_cap)
@@ -829,7 +957,11 @@ static int integrate_host (b200tsdf* h, const void* points, size_t stride, int x
   }
   // double-buffered upload on the copy stream: frame i+1 crosses PCIe while frame i is fused
   int b = (int) (h->frame_no & 1);
-  if (h->frame_no >= 2) CK (cudaStreamWaitEvent (h->copy_stream, h->ev_consumed[b], 0));
+  if (h->frame_no >= 2)
+  {
+    CK (cudaEventSynchronize (h->ev_copied[b]));           // the upload of frame i-2 has left the caller's buffer (the documented contract)
+    CK (cudaStreamWaitEvent (h->copy_stream, h->ev_consumed[b], 0));
+  }
   CK (cudaMemcpyAsync (h->d_frame[b], points, bytes, cudaMemcpyHostToDevice, h->copy_stream));
   h->h2d_bytes += (long long) bytes;
   CK (cudaEventRecord (h->ev_copied[b], h->copy_stream));
@@ -997,8 +1129,9 @@ int b200tsdf_query (b200tsdf_t* h, const float* xyz, int n, int what, int mode,
   if (what & 1) CK (cudaMemcpyAsync (val, d_val, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
   if (what & 2) CK (cudaMemcpyAsync (grad, d_grad, (size_t) n * 12, cudaMemcpyDeviceToHost, s));
   if (what & 4) CK (cudaMemcpyAsync (hess, d_hess, (size_t) n * 36, cudaMemcpyDeviceToHost, s));
+  note_device_err (h, s);
   CK (cudaStreamSynchronize (s));
-  return B200TSDF_OK;
+  return pending_device_err (h);
 }
 
 // ---- renderView / renderColoredView (tsdf_volume_octree.cpp:278-450) ----------------------------------
@@ -1007,6 +1140,8 @@ int b200tsdf_render (b200tsdf_t* h, const double* pose, int downsample, void* ou
 {
   if (!h || !pose || !out || downsample < 1) return B200TSDF_EINVAL;
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "renderView before reset()");
+  if (stride < 12 || xyz_off < 0 || normal_off < 0 || (size_t) xyz_off + 12 > stride || (size_t) normal_off + 12 > stride)
+    return h->fail (B200TSDF_EINVAL, "bad output point layout (need xyz_off + 12 <= stride and normal_off + 12 <= stride)");
   cudaSetDevice (h->device);
   const Params& p = h->p;
   RenderParams r;
@@ -1022,7 +1157,9 @@ int b200tsdf_render (b200tsdf_t* h, const double* pose, int downsample, void* ou
   std::vector<float> tmp (npix * 6);
   CK (cudaMemcpyAsync (tmp.data (), d_out, npix * 6 * sizeof (float), cudaMemcpyDeviceToHost, s));
   if (rgb_out) CK (cudaMemcpyAsync (rgb_out, d_rgb, npix * 3, cudaMemcpyDeviceToHost, s));
+  note_device_err (h, s);
   CK (cudaStreamSynchronize (s));
+  if (int rc = pending_device_err (h)) return rc;
   unsigned char* base = (unsigned char*) out;
   for (size_t i = 0; i < npix; ++i)
   {
@@ -1130,17 +1267,17 @@ extern "C" {
 // [6..10] slow level-2 nodes, slow level-1 nodes, cell leaf visits, cell fall-throughs, cells folded).
 int b200tsdf_debug_timing (b200tsdf_t* h, unsigned long long* out16)
 {
-  static unsigned long long* d_dbg = nullptr;
   if (!h || !out16) return B200TSDF_EINVAL;
   cudaSetDevice (h->device);
   CK (cudaStreamSynchronize (h->stream));
-  if (!d_dbg)
+  if (!h->d_dbg)
   {
-    CK (cudaMalloc (&d_dbg, 16 * 8)); CK (cudaMemset (d_dbg, 0, 16 * 8));
-    CK (cudaMemcpyToSymbol (g_dbg, &d_dbg, sizeof (d_dbg)));
+    CK (cudaMalloc (&h->d_dbg, 16 * 8)); CK (cudaMemset (h->d_dbg, 0, 16 * 8));
+    h->p.dbg = h->d_dbg;                                   // armed from the next frame on (this handle only)
+    drop_batch_graphs (h);
   }
-  CK (cudaMemcpy (out16, d_dbg, 16 * 8, cudaMemcpyDeviceToHost));
-  CK (cudaMemset (d_dbg, 0, 16 * 8));
+  CK (cudaMemcpy (out16, h->d_dbg, 16 * 8, cudaMemcpyDeviceToHost));
+  CK (cudaMemset (h->d_dbg, 0, 16 * 8));
   return B200TSDF_OK;
 }
 
@@ -1153,6 +1290,7 @@ int b200tsdf_profile_begin (b200tsdf_t* h)
   CK (cudaStreamSynchronize (h->stream));
   h->drain_kring (0);
   h->prof_ms_kernel = 0; h->prof_kernel_launches = 0; h->prof_frames = 0;
+  h->time_frames = true; h->prof_graph0 = h->graph_launches;
   h->prof_launch0 = h->launches; h->prof_h2d0 = h->h2d_bytes; h->prof_d2h0 = h->d2h_bytes;
   CK (cudaMemcpy (h->prof_stats0, h->d_stats, sizeof (h->prof_stats0), cudaMemcpyDeviceToHost));
   CK (cudaEventRecord (h->ev_p0, h->stream));
@@ -1178,6 +1316,10 @@ int b200tsdf_profile_end (b200tsdf_t* h, b200tsdf_profile* out)
   out->n_frames = h->prof_frames;
   out->n_updates = (int64_t) (st[ST_UPDATES] - h->prof_stats0[ST_UPDATES]);
   out->n_node_visits = (int64_t) (st[ST_VISITS] - h->prof_stats0[ST_VISITS]);
+  out->ms_kernel_device = 1e-6 * (double) (st[5] - h->prof_stats0[5]);
+  out->kernel_launches_device = (int64_t) (st[6] - h->prof_stats0[6]);
+  out->graph_launches = h->graph_launches - h->prof_graph0;
+  h->time_frames = false;
   out->h2d_bytes = h->h2d_bytes - h->prof_h2d0; out->d2h_bytes = h->d2h_bytes - h->prof_d2h0;
   return check_device_err (h);
 }

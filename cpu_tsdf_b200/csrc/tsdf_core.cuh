@@ -157,6 +157,8 @@ struct Params
   float* root_M;
   int* root_ns;
   int* err;                   // device error bits
+  unsigned long long* diag;   // [0] slow folds in the upper sweeps, [1] visits inside them (this handle's counters; may be null)
+  unsigned long long* dbg;    // optional phase timing of k_celltop_up (b200tsdf_debug_timing), normally null
 };
 
 struct Frame

@@ -80,9 +80,20 @@ int  b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int x
  * handle's stream; call b200tsdf_sync before reading results on the host) */
 int  b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t stride, int xyz_off, int rgba_off,
                                 int width, int height, const double* pose_c2w);
+/* n consecutive integrateCloud calls (hpp:48-103) on clouds resident in device memory, fused in order: the frame
+ * parameters go to the device in one copy and the launches of the whole batch are one CUDA-graph launch (captured once
+ * per batch size, replayed afterwards), so the host issues ~3 driver calls per batch instead of ~6 per frame.
+ * d_points: n device pointers (same layout for all); poses_c2w: n row-major 4x4 matrices back to back.  Asynchronous
+ * like b200tsdf_integrate_device.  Grid shapes without a replayable launch sequence are fused frame by frame. */
+int  b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_points, size_t stride, int xyz_off, int rgba_off,
+                                      int width, int height, const double* poses_c2w);
 /* streaming variant of b200tsdf_integrate for producers that keep their (pinned) frame buffers alive:
  * returns as soon as the copy and the kernels are enqueued.  `points` must stay valid and unmodified
- * until b200tsdf_sync() or until two further frames have been submitted on this handle. */
+ * until b200tsdf_sync() or until two further frames have been submitted on this handle (the call that submits
+ * frame i+2 waits for the upload of frame i before it returns).
+ * Error reporting of the asynchronous entry points (integrate_device / _batch_device / _async, and integrate itself, which
+ * waits for its upload only): a device-side failure of frame i (brick pool exhausted, work queue overflow) is reported by
+ * the next call on the handle (integrate*, query, render) and at the latest by sync / get_stats / mesh / save. */
 int  b200tsdf_integrate_async (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
                                int width, int height, const double* pose_c2w);
 int  b200tsdf_sync (b200tsdf_t* h);
@@ -206,6 +217,9 @@ typedef struct b200tsdf_profile
   int64_t n_updates;         /* sum over frames of voxels whose {sdf,weight} changed                  */
   int64_t n_node_visits;
   int64_t h2d_bytes, d2h_bytes; /* bytes this library copied across PCIe in the region                */
+  double  ms_kernel_device;  /* the same kernel timed on the device (%globaltimer, first block start -> last block end):  */
+  int64_t kernel_launches_device; /* also available for frames replayed from a CUDA graph, where no event can be placed   */
+  int64_t graph_launches;    /* cudaGraphLaunch calls in the region (b200tsdf_integrate_batch_device)                      */
 } b200tsdf_profile;
 int  b200tsdf_profile_begin (b200tsdf_t* h);
 int  b200tsdf_profile_end (b200tsdf_t* h, b200tsdf_profile* out);

@@ -356,3 +356,31 @@ def test_shards_gathered_into_one_volume_render_like_the_whole():
         other = pkg.TSDFVolumeOctree(device=0, pool_log2=12)
         other.setResolution(256, 256, 256); other.reset()
         other.import_shard(shards[0].export_shard())          # different grid
+
+
+def test_batch_graph_replay_matches_the_oracle_and_frame_by_frame():
+    """b200tsdf_integrate_batch_device: the frames of a batch are replayed from one captured CUDA graph (records in a device
+    ring).  Three batches (sizes 5, 5, 3: the second replays the first one's graph on the other half of the ring) must leave
+    exactly the volume the oracle builds frame by frame."""
+    import torch
+    o, e = pair(CFG_512, 18, integrate_color=1)
+    fs = list(frames(synth.S1, 13, stride=7, color=True, noise_seed=21))
+    dev = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for _, c in fs]
+    for pose, cloud in fs:
+        o.integrate(cloud, pose)
+    H, W = fs[0][1].shape[:2]
+    for lo, hi in ((0, 5), (5, 10), (10, 13)):
+        assert fs[0][1].shape[2] == 8                                  # pcl::PointXYZRGBA rows
+        e.integrateBatchDevice([d.data_ptr() for d in dev[lo:hi]], H, W, 32, [p for p, _ in fs[lo:hi]], rgba_off=16)
+    e.sync()
+    assert_same_nodes(o.dump_nodes(), e.download_nodes(), rgb=True)
+    assert e.stats().n_updates == o.stats().n_add_observation
+    # a grid shape without a replayable launch sequence takes the frame-by-frame route inside the same call
+    o2, e2 = pair(CFG_256, 16)
+    fs2 = list(frames(synth.S1, 3, stride=9, noise_seed=5))
+    dev2 = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for _, c in fs2]
+    for pose, cloud in fs2:
+        o2.integrate(cloud, pose)
+    e2.integrateBatchDevice([d.data_ptr() for d in dev2], H, W, 4 * fs2[0][1].shape[2], [p for p, _ in fs2])
+    e2.sync()
+    assert_same_nodes(o2.dump_nodes(), e2.download_nodes())
