@@ -119,6 +119,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(gpu):
+    """Run this process (and first-touch its pinned buffers) on the CPU cores local to the GPU: on a two-socket host a
+    pinned buffer on the far socket costs a large part of the PCIe bandwidth the end-to-end leg is bound by."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        avail = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in avail]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} GPU-local cores ({cpus[0]}..{cpus[-1]})"
+    except Exception as e:            # no NVML, a container without the call, ...: keep the default placement
+        return f"default ({type(e).__name__})"
+    return "default"
+
+
 def oracle_volume(kind):
     from oracle.oracle_py import OracleVolume
     return OracleVolume(kind=kind, xres=RES, yres=RES, zres=RES, xsize=SIZE, ysize=SIZE, zsize=SIZE,
@@ -248,6 +268,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -404,7 +425,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": int(prof_e.h2d_bytes // args.steps), "d2h_bytes_per_step": int(prof_e.d2h_bytes // args.steps),
-                    "timing": "max(CUDA events on the engine stream, host wall clock) over ranks"},
+                    "timing": "max(CUDA events on the engine stream, host wall clock) over ranks", "host_affinity": affinity},
             "gpu_launches": int(prof.total_launches),
             "graph_launches": int(prof.graph_launches),
             "host_load_leg": host_load,

@@ -42,6 +42,12 @@ struct FrameRec
 __device__ __forceinline__ unsigned long long global_ns () { unsigned long long t; asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 constexpr int MAX_QLEVELS = 8;
+// Block roots are queued in BL_CLASSES lists by expected work (the number of interior level-2 nodes the brick had in the
+// previous frame: its finest rounds), heaviest class first, so that the short bricks fill the tail of the brick kernel.
+// Counter slots of a frame's set: class 0 = 9, classes 1.. = 12, 13, 14.
+constexpr int BL_CLASSES = 4;
+__host__ __device__ __forceinline__ int bl_count_slot (int c) { return c == 0 ? 9 : 11 + c; }
+__device__ __forceinline__ int bl_class (int work) { return (work < 28) + (work < 16) + (work < 6); }
 struct Queues
 {
   QNode* q[MAX_QLEVELS];    // q[i] holds level C+i
@@ -989,7 +995,7 @@ __device__ __forceinline__ void top_kj (int f, int& k, int& j)
 template <bool COLOR>
 __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const FrameRec* __restrict__ fr, const QNode* __restrict__ cells, int* __restrict__ d_count,
                                                                QNode* __restrict__ gq, CellTop* __restrict__ tops, int cell_cap,
-                                                               int* __restrict__ blist, unsigned long long* __restrict__ stats)
+                                                               int* __restrict__ blist, int bl_stride, unsigned long long* __restrict__ stats)
 {
   __shared__ __align__ (16) TopSmem S;
   __shared__ Frame s_f_;
@@ -999,7 +1005,6 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
     for (int w_ = tid; w_ < (int) (sizeof (Frame) / sizeof (int)); w_ += TOP_THREADS) dst_[w_] = src_[w_];
   }
   int* const cnt_ = d_count + 16 * fr->cset;
-  int* const bcount = cnt_ + 9;
   __syncthreads ();
   const Frame& f = s_f_;
   unsigned long long upd = 0, vis = 0;
@@ -1123,14 +1128,19 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
         gq[(size_t) ci * STRIDE + 73 + j3] = e;
       }
       const bool push = interior && bslot >= 0;
-      const unsigned mask = __ballot_sync (0xffffffffu, push);
-      if (mask)
+      const int cls = push ? bl_class (p.work[bslot]) : -1;
+#pragma unroll
+      for (int c = 0; c < BL_CLASSES; ++c)
       {
-        int b = 0;
-        const int leader = __ffs (mask) - 1;
-        if (lane == leader) b = atomicAdd (bcount, __popc (mask));
-        b = __shfl_sync (0xffffffffu, b, leader);
-        if (push) blist[b + __popc (mask & ((1u << lane) - 1))] = ci * STRIDE + 73 + j3;
+        const unsigned mask = __ballot_sync (0xffffffffu, cls == c);
+        if (mask)
+        {
+          int b = 0;
+          const int leader = __ffs (mask) - 1;
+          if (lane == leader) b = atomicAdd (cnt_ + bl_count_slot (c), __popc (mask));
+          b = __shfl_sync (0xffffffffu, b, leader);
+          if (cls == c) blist[(size_t) c * bl_stride + b + __popc (mask & ((1u << lane) - 1))] = ci * STRIDE + 73 + j3;
+        }
       }
     }
     // ---- write back what changed, and the scratch for the bottom-up sweep ----

@@ -443,6 +443,7 @@ namespace {
 
 void free_volume (b200tsdf* h)
 {
+  cudaFree (h->p.work); h->p.work = nullptr;
   cudaFree (h->p.keys); cudaFree (h->p.nodes); cudaFree (h->p.split); cudaFree (h->p.rgb); cudaFree (h->p.M); cudaFree (h->p.ns);
   cudaFree (h->p.root_dw); cudaFree (h->p.root_split); cudaFree (h->p.root_rgb); cudaFree (h->p.root_M); cudaFree (h->p.root_ns);
   h->p.keys = nullptr; h->p.nodes = nullptr; h->p.split = nullptr; h->p.rgb = nullptr; h->p.M = nullptr; h->p.ns = nullptr;
@@ -608,6 +609,7 @@ int b200tsdf_reset (b200tsdf_t* h)
     CK (cudaMalloc (&h->p.keys, pool * sizeof (uint64_t)));
     CK (cudaMalloc (&h->p.nodes, pool * BRICK_NODES * sizeof (float2)));
     CK (cudaMalloc (&h->p.split, pool * BRICK_SPLIT_WORDS * sizeof (uint32_t)));
+    CK (cudaMalloc (&h->p.work, pool));
     if (color) CK (cudaMalloc (&h->p.rgb, pool * BRICK_NODES * sizeof (uchar4)));
     if (var) { CK (cudaMalloc (&h->p.M, pool * BRICK_NODES * sizeof (float))); CK (cudaMalloc (&h->p.ns, pool * BRICK_NODES * sizeof (int))); }
     CK (cudaMalloc (&h->p.root_dw, root_n * sizeof (float2)));
@@ -671,7 +673,7 @@ int b200tsdf_reset (b200tsdf_t* h)
     if (bl > h->blist_cap)
     {
       cudaFree (h->d_blist); cudaFree (h->d_bail); h->d_blist = h->d_bail = nullptr; h->blist_cap = 0;
-      CK (cudaMalloc (&h->d_blist, bl * sizeof (int)));
+      CK (cudaMalloc (&h->d_blist, bl * BL_CLASSES * sizeof (int)));          // one list per work class
       CK (cudaMalloc (&h->d_bail, bl * sizeof (int)));
       h->blist_cap = bl;
     }
@@ -681,6 +683,7 @@ int b200tsdf_reset (b200tsdf_t* h)
     // keep the storage pointers, take every scalar from the derived set
     Params st = p;
     p = np;
+    p.work = st.work;
     p.keys = st.keys; p.nodes = st.nodes; p.split = st.split; p.rgb = st.rgb; p.M = st.M; p.ns = st.ns;
     p.root_dw = st.root_dw; p.root_split = st.root_split; p.root_rgb = st.root_rgb; p.root_M = st.root_M; p.root_ns = st.root_ns;
   }
@@ -693,6 +696,7 @@ int b200tsdf_reset (b200tsdf_t* h)
   cudaStream_t s = h->stream;
   CK (cudaMemsetAsync (p.keys, 0, pool * sizeof (uint64_t), s));
   CK (cudaMemsetAsync (p.split, 0, pool * BRICK_SPLIT_WORDS * sizeof (uint32_t), s));
+  CK (cudaMemsetAsync (p.work, 0, pool, s));
   k_fill_fresh<<<148 * 8, 256, 0, s>>> (p.nodes, pool * BRICK_NODES);
   if (color) CK (cudaMemsetAsync (p.rgb, 0, pool * BRICK_NODES * sizeof (uchar4), s));
   if (var) { CK (cudaMemsetAsync (p.M, 0, pool * BRICK_NODES * sizeof (float), s)); CK (cudaMemsetAsync (p.ns, 0, pool * BRICK_NODES * sizeof (int), s)); }
@@ -764,8 +768,8 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
       bli = NL;
       if (h->top_path)
       {
-        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, h->d_stats);
-        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, h->d_stats);
+        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats);
+        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats);
       }
       else if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
@@ -779,13 +783,13 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
     (void) d_bailcount;
     if (h->bd_minb == 6)
     {
-      if (p.color) k_bricks<true, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
-      else k_bricks<false, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+      if (p.color) k_bricks<true, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
+      else k_bricks<false, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
     }
     else
     {
-      if (p.color) k_bricks<true, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
-      else k_bricks<false, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, h->d_count, h->d_stats, p.L - 3);
+      if (p.color) k_bricks<true, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
+      else k_bricks<false, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
     }
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;

@@ -156,6 +156,7 @@ struct Params
   uchar4* root_rgb;
   float* root_M;
   int* root_ns;
+  unsigned char* work;        // [pool] finest-tier bricks: interior level-2 nodes seen by the last update (scheduling hint only)
   int* err;                   // device error bits
   unsigned long long* diag;   // [0] slow folds in the upper sweeps, [1] visits inside them (this handle's counters; may be null)
   unsigned long long* dbg;    // optional phase timing of k_celltop_up (b200tsdf_debug_timing), normally null
