@@ -240,7 +240,8 @@ def workload_config(frames_per_step, n_gpus):
             "frames_per_step": frames_per_step, "image": [W, H], "grid": RES, "grid_size_m": SIZE,
             "point_bytes": 32, "distinct_frames": N_DISTINCT,
             "l2": "inputs larger than L2 (64 distinct frames = 629 MB device-resident, orbit covers a >126 MB brick working set)",
-            "parallelism": "1 GPU" if n_gpus == 1 else f"volume sharded by coarse cell over {n_gpus} GPUs, every rank integrates every frame"}
+            "parallelism": "1 GPU" if n_gpus == 1 else f"volume sharded by coarse cell over {n_gpus} GPUs, every rank integrates every frame "
+                           f"(end to end: each rank uploads 1/{n_gpus} of every frame, NVLink all-gather)"}
 
 
 def main():
@@ -268,6 +269,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
     affinity = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -287,8 +289,15 @@ def main():
 
     # device-resident inputs (torch owns the memory; the engine reads it through the C ABI)
     d_clouds = [torch.from_numpy(c).cuda() for c in clouds]
-    # pinned host inputs for the end-to-end leg
-    h_clouds = [torch.from_numpy(c).pin_memory() for c in clouds]
+    # pinned host inputs for the end-to-end leg: a rank's host memory holds only ITS row slice of every frame (at N = 1 the
+    # whole frame); the library uploads the slice over this GPU's PCIe link and all-gathers the frame over NVLink
+    if world > 1:
+        ids = [pkg.TSDFVolumeOctree.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        vol.commInit(ids[0], rank, world)
+    row0, row1 = vol.rowSlice(H)
+    h_rows = [torch.from_numpy(np.ascontiguousarray(c[row0:row1])).pin_memory() for c in clouds]
+    h_ptrs = [t.data_ptr() for t in h_rows]
     torch.cuda.synchronize()
     stride = 32
 
@@ -306,10 +315,9 @@ def main():
             vol.integrateCloudDevice(d_ptrs[i], H, W, stride, poses[i], rgba_off=16)
 
     def step_host(k0):
-        for j in range(FRAMES_PER_STEP):
-            i = (k0 + j) % N_DISTINCT
-            h = h_clouds[i]
-            vol.integrateCloudAsync(h.data_ptr(), H, W, stride, poses[i], rgba_off=16)   # pinned buffer stays alive
+        # public API with HOST buffers: slice upload (H2D) + NVLink all-gather + one graph launch for the step's 32 frames
+        idx = [(k0 + j) % N_DISTINCT for j in range(FRAMES_PER_STEP)]
+        vol.integrateBatchRows([h_ptrs[i] for i in idx], H, W, stride, [poses[i] for i in idx], rgba_off=16)
         return vol.stats().n_updates         # D2H read of the step's result (synchronizes)
 
     def timed(step_fn, steps):
@@ -414,6 +422,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, all_cpus)                 # the CPU arm gets every host core again
             nproc = os.cpu_count() or 1
             tl = sorted({1, min(4, nproc), nproc})
             cpu = cpu_arm(poses, clouds, 12, tl)
@@ -425,6 +434,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": int(prof_e.h2d_bytes // args.steps), "d2h_bytes_per_step": int(prof_e.d2h_bytes // args.steps),
+                    "nvlink_bytes_per_step": int(prof_e.nvlink_bytes // args.steps),
+                    "path": "b200tsdf_integrate_batch_rows: each rank uploads rows [%d, %d) of every frame from pinned host memory, packs to 16 B pixels, "
+                            "NCCL all-gather over NVLink, one graph launch per 32 frames" % (row0, row1),
                     "timing": "max(CUDA events on the engine stream, host wall clock) over ranks", "host_affinity": affinity},
             "gpu_launches": int(prof.total_launches),
             "graph_launches": int(prof.graph_launches),

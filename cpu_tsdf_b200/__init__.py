@@ -59,6 +59,7 @@ class Profile(C.Structure):
         ("kernel_launches", C.c_int64), ("total_launches", C.c_int64), ("n_frames", C.c_int64),
         ("n_updates", C.c_int64), ("n_node_visits", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_kernel_device", C.c_double), ("kernel_launches_device", C.c_int64), ("graph_launches", C.c_int64),
+        ("nvlink_bytes", C.c_int64),
     ]
 
 
@@ -70,7 +71,8 @@ class OrganizeOpts(C.Structure):
 EXPORTS = [
     "b200tsdf_default_config", "b200tsdf_create", "b200tsdf_destroy", "b200tsdf_last_error",
     "b200tsdf_set_config", "b200tsdf_get_config", "b200tsdf_reset", "b200tsdf_integrate",
-    "b200tsdf_integrate_device", "b200tsdf_integrate_batch_device", "b200tsdf_integrate_async", "b200tsdf_sync", "b200tsdf_organize", "b200tsdf_integrate_unorganized", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
+    "b200tsdf_integrate_device", "b200tsdf_integrate_batch_device", "b200tsdf_integrate_async",
+    "b200tsdf_comm_unique_id", "b200tsdf_comm_init", "b200tsdf_row_slice", "b200tsdf_integrate_batch_rows", "b200tsdf_gather_volume", "b200tsdf_sync", "b200tsdf_organize", "b200tsdf_integrate_unorganized", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
     "b200tsdf_free", "b200tsdf_save", "b200tsdf_load", "b200tsdf_export_shard", "b200tsdf_import_shard", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
     "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_frustum_cull",
     "b200tsdf_profile_begin", "b200tsdf_profile_end",
@@ -102,6 +104,11 @@ def load_library() -> C.CDLL:
     lib.b200tsdf_integrate_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_integrate_async.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.b200tsdf_integrate_batch_device.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.b200tsdf_comm_unique_id.argtypes = [vp]
+    lib.b200tsdf_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.b200tsdf_row_slice.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.b200tsdf_integrate_batch_rows.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.b200tsdf_gather_volume.argtypes = [vp, vp, C.c_int]
     lib.b200tsdf_sync.argtypes = [vp]
     szp = C.POINTER(C.c_size_t)
     lib.b200tsdf_mesh_flatten.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_float, C.POINTER(vp), szp, C.POINTER(vp), szp]
@@ -278,6 +285,36 @@ class TSDFVolumeOctree:
         ps = np.ascontiguousarray(np.stack([np.asarray(_pose(t)).reshape(4, 4) for t in poses]), dtype=np.float64)
         self._check(self._lib.b200tsdf_integrate_batch_device(self._h, n, arr, stride, 0, rgba_off, width, height, _ptr(ps)))
         return True
+
+    # ---- multi-GPU data paths (one process per GPU; NCCL over NVLink inside the library) ----
+    @staticmethod
+    def commUniqueId() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().b200tsdf_comm_unique_id(buf)
+        if rc:
+            raise B200Error(f"b200tsdf_comm_unique_id failed ({rc}): NCCL not loadable")
+        return buf.raw
+
+    def commInit(self, unique_id: bytes, rank: int, nranks: int):
+        self._check(self._lib.b200tsdf_comm_init(self._h, C.create_string_buffer(unique_id, 128), rank, nranks))
+
+    def rowSlice(self, height: int):
+        r0, r1 = C.c_int(0), C.c_int(0)
+        self._check(self._lib.b200tsdf_row_slice(self._h, height, C.byref(r0), C.byref(r1)))
+        return r0.value, r1.value
+
+    def integrateBatchRows(self, row_ptrs, height: int, width: int, stride: int, poses, rgba_off: int = -1) -> bool:
+        """len(row_ptrs) <= 32 frames of which this rank's HOST memory holds only its row slice (rowSlice): upload over this GPU's
+        PCIe link, all-gather over NVLink, fuse (collective: every rank calls it with the same frames)."""
+        n = len(row_ptrs)
+        arr = (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in row_ptrs])
+        ps = np.ascontiguousarray(np.stack([np.asarray(_pose(t)).reshape(4, 4) for t in poses]), dtype=np.float64)
+        self._check(self._lib.b200tsdf_integrate_batch_rows(self._h, n, arr, stride, 0, rgba_off, width, height, _ptr(ps)))
+        return True
+
+    def gatherVolume(self, full, root: int = 0):
+        """Collective: all shards -> `full` (a reset, unsharded volume on the root's device; None on the other ranks), device to device."""
+        self._check(self._lib.b200tsdf_gather_volume(self._h, None if full is None else full._h, root))
 
     def sync(self):
         self._check(self._lib.b200tsdf_sync(self._h))

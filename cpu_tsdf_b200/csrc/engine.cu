@@ -391,7 +391,7 @@ struct b200tsdf
   // fused per-cell upper sweeps (coarse cells are the top-tier roots and the block roots are <= 3 levels below)
   bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0; CellTop* d_celltop = nullptr; bool top_path = false;
   bool fast_path = false; int force_general = 0;
-  int bd_minb = 8;               // resident CTAs per SM the brick kernel is compiled for (tuning knob: B200TSDF_BD_MINB=6|8)
+  int bd_minb = 6;               // resident CTAs per SM the brick kernel is compiled for (80 registers; tuning knob: B200TSDF_BD_MINB=6|8)
   // device copy of Params (the rare out-of-line paths read it through a pointer) and the ring of per-frame records
   Params* d_params = nullptr;
   unsigned long long* d_dbg = nullptr;     // phase-timing counters of k_celltop_up once b200tsdf_debug_timing armed them
@@ -403,6 +403,13 @@ struct b200tsdf
   FrameRec* d_bring = nullptr; FrameRec* h_bring = nullptr; int bring_half = 0; bool bring_used[2] = { false, false };
   cudaEvent_t ev_bring[2] = { nullptr, nullptr };
   cudaGraphExec_t batch_exec[2][FRAME_RING / 2 + 1] = {};
+  // multi-GPU (multigpu.cuh): NCCL communicator (opaque here), row-sliced uploads
+  void* comm = nullptr; int comm_rank = 0, comm_size = 1;
+  unsigned char* d_rows_raw[2] = { nullptr, nullptr }; unsigned char* d_rows_full[2] = { nullptr, nullptr };
+  size_t rows_raw_cap = 0, rows_full_cap = 0; int rows_set = 0; bool rows_used[2] = { false, false };
+  int rows_chunk = 4;            // frames per upload/fuse pipeline stage of b200tsdf_integrate_batch_rows (B200TSDF_ROWS_CHUNK=2..32)
+  cudaEvent_t ev_rows_ready[2][16] = {}, ev_rows_done[2] = { nullptr, nullptr };
+  long long nvlink_bytes = 0, prof_nvlink0 = 0;
   int launches_per_frame = 0; long long graph_launches = 0, prof_graph0 = 0;
   // measurement
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
@@ -450,6 +457,8 @@ void free_volume (b200tsdf* h)
   h->p.root_dw = nullptr; h->p.root_split = nullptr; h->p.root_rgb = nullptr; h->p.root_M = nullptr; h->p.root_ns = nullptr;
   h->pool = 0; h->root_n = 0;
 }
+
+void comm_release (b200tsdf* h);          // multigpu.cuh
 
 void drop_batch_graphs (b200tsdf* h)
 {
@@ -506,7 +515,8 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   b200tsdf* h = new b200tsdf;
   if (cfg) h->cfg_pending = *cfg; else b200tsdf_default_config (&h->cfg_pending);
   h->device = h->cfg_pending.device;
-  if (const char* e = std::getenv ("B200TSDF_BD_MINB")) { if (std::atoi (e) == 6) h->bd_minb = 6; }
+  if (const char* e = std::getenv ("B200TSDF_ROWS_CHUNK")) { const int v = std::atoi (e); if (v >= 2 && v <= 32) h->rows_chunk = v; }
+  if (const char* e = std::getenv ("B200TSDF_BD_MINB")) { const int v = std::atoi (e); if (v == 6 || v == 8) h->bd_minb = v; }
   if (h->device < 0 || h->device >= ndev) { delete h; return B200TSDF_EINVAL; }
   bool ok = cudaSetDevice (h->device) == cudaSuccess
          && cudaDeviceGetAttribute (&h->sm_count, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess
@@ -523,6 +533,8 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
          && cudaEventCreateWithFlags (&h->ev_ring[1], cudaEventDisableTiming) == cudaSuccess
          && cudaMalloc (&h->d_bring, FRAME_RING * sizeof (FrameRec)) == cudaSuccess
          && cudaHostAlloc (&h->h_bring, FRAME_RING * sizeof (FrameRec), cudaHostAllocDefault) == cudaSuccess
+         && cudaEventCreateWithFlags (&h->ev_rows_done[0], cudaEventDisableTiming) == cudaSuccess
+         && cudaEventCreateWithFlags (&h->ev_rows_done[1], cudaEventDisableTiming) == cudaSuccess
          && cudaEventCreateWithFlags (&h->ev_bring[0], cudaEventDisableTiming) == cudaSuccess
          && cudaEventCreateWithFlags (&h->ev_bring[1], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i)
@@ -531,6 +543,7 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   ok = ok && cudaEventCreate (&h->ev_t0) == cudaSuccess && cudaEventCreate (&h->ev_t1) == cudaSuccess
           && cudaEventCreate (&h->ev_k0) == cudaSuccess && cudaEventCreate (&h->ev_k1) == cudaSuccess
           && cudaEventCreate (&h->ev_p0) == cudaSuccess && cudaEventCreate (&h->ev_p1) == cudaSuccess;
+  for (int i = 0; ok && i < 32; ++i) ok = cudaEventCreateWithFlags (&h->ev_rows_ready[i / 16][i % 16], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < KRING; ++i)
     ok = cudaEventCreate (&h->kring[i][0]) == cudaSuccess && cudaEventCreate (&h->kring[i][1]) == cudaSuccess;
   if (ok) *h->h_err = 0;
@@ -554,6 +567,13 @@ void b200tsdf_destroy (b200tsdf_t* h)
   cudaFree (h->d_params); cudaFree (h->d_ring); if (h->h_ring) cudaFreeHost (h->h_ring);
   for (int i = 0; i < 2; ++i) if (h->ev_ring[i]) cudaEventDestroy (h->ev_ring[i]);
   drop_batch_graphs (h);
+  comm_release (h);
+  for (int i = 0; i < 2; ++i)
+  {
+    cudaFree (h->d_rows_raw[i]); cudaFree (h->d_rows_full[i]);
+    for (int k = 0; k < 16; ++k) if (h->ev_rows_ready[i][k]) cudaEventDestroy (h->ev_rows_ready[i][k]);
+    if (h->ev_rows_done[i]) cudaEventDestroy (h->ev_rows_done[i]);
+  }
   cudaFree (h->d_bring); if (h->h_bring) cudaFreeHost (h->h_bring);
   for (int i = 0; i < 2; ++i) if (h->ev_bring[i]) cudaEventDestroy (h->ev_bring[i]);
   cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop);
@@ -1294,7 +1314,7 @@ int b200tsdf_profile_begin (b200tsdf_t* h)
   CK (cudaStreamSynchronize (h->stream));
   h->drain_kring (0);
   h->prof_ms_kernel = 0; h->prof_kernel_launches = 0; h->prof_frames = 0;
-  h->time_frames = true; h->prof_graph0 = h->graph_launches;
+  h->time_frames = true; h->prof_graph0 = h->graph_launches; h->prof_nvlink0 = h->nvlink_bytes;
   h->prof_launch0 = h->launches; h->prof_h2d0 = h->h2d_bytes; h->prof_d2h0 = h->d2h_bytes;
   CK (cudaMemcpy (h->prof_stats0, h->d_stats, sizeof (h->prof_stats0), cudaMemcpyDeviceToHost));
   CK (cudaEventRecord (h->ev_p0, h->stream));
@@ -1323,6 +1343,7 @@ int b200tsdf_profile_end (b200tsdf_t* h, b200tsdf_profile* out)
   out->ms_kernel_device = 1e-6 * (double) (st[5] - h->prof_stats0[5]);
   out->kernel_launches_device = (int64_t) (st[6] - h->prof_stats0[6]);
   out->graph_launches = h->graph_launches - h->prof_graph0;
+  out->nvlink_bytes = h->nvlink_bytes - h->prof_nvlink0;
   h->time_frames = false;
   out->h2d_bytes = h->h2d_bytes - h->prof_h2d0; out->d2h_bytes = h->d2h_bytes - h->prof_d2h0;
   return check_device_err (h);
@@ -1823,3 +1844,5 @@ int b200tsdf_import_shard (b200tsdf_t* h, const void* buf, size_t nbytes)
 
 } // extern "C"
 
+
+#include "multigpu.cuh"

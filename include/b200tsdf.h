@@ -183,6 +183,25 @@ int  b200tsdf_load (b200tsdf_t* h, const char* path);
 int  b200tsdf_export_shard (b200tsdf_t* h, void* buf, size_t capacity, size_t* nbytes);
 int  b200tsdf_import_shard (b200tsdf_t* h, const void* buf, size_t nbytes);
 
+/* ---- multi-GPU data paths (one process per GPU).  NCCL is loaded at run time; without it these return
+ * B200TSDF_ESTATE.  b200tsdf_comm_unique_id: 128 bytes, created on one rank and handed to the others by any means;
+ * b200tsdf_comm_init: collective, binds the handle to a communicator of `nranks` ranks (normally shard_rank / shard_count). */
+int  b200tsdf_comm_unique_id (void* id128);
+int  b200tsdf_comm_init (b200tsdf_t* h, const void* id128, int rank, int nranks);
+/* rows [*row0, *row1) of a `height`-row frame are this rank's slice (ceil(height / nranks) rows per rank) */
+int  b200tsdf_row_slice (const b200tsdf_t* h, int height, int* row0, int* row1);
+/* n <= 32 consecutive integrateCloud calls where this rank's HOST memory holds only its row slice of every frame
+ * (rows[i] -> points (v * width + u), v in the slice; layout as for b200tsdf_integrate).  The slice is uploaded over this
+ * GPU's PCIe link, packed to 16-byte pixels and all-gathered over NVLink into the full frame on every rank (collective: all
+ * ranks call with the same n), then the batch is fused like b200tsdf_integrate_batch_device.  Without a communicator the
+ * slice is the whole frame and nothing is exchanged.  rows[i] must stay valid until b200tsdf_sync or two further calls. */
+int  b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows, size_t stride, int xyz_off, int rgba_off,
+                                    int width, int height, const double* poses_c2w);
+/* Collective: every rank's shard goes device to device (NCCL send/recv over NVLink, no host staging) to rank `root`, which
+ * merges them into `full` — a handle on the root's device with shard_count 1 and the same grid, already reset (NULL on the
+ * other ranks).  renderView / queries / marching cubes then run on `full` (reads across shards are replicas only). */
+int  b200tsdf_gather_volume (b200tsdf_t* h, b200tsdf_t* full, int root);
+
 /* getVoxelCenter / getVoxelIndex (cpp:553-574) */
 int  b200tsdf_voxel_center (const b200tsdf_t* h, int64_t x, int64_t y, int64_t z, float* out3);
 int  b200tsdf_voxel_index (const b200tsdf_t* h, float x, float y, float z, int32_t* out3, int32_t* inside);
@@ -220,6 +239,7 @@ typedef struct b200tsdf_profile
   double  ms_kernel_device;  /* the same kernel timed on the device (%globaltimer, first block start -> last block end):  */
   int64_t kernel_launches_device; /* also available for frames replayed from a CUDA graph, where no event can be placed   */
   int64_t graph_launches;    /* cudaGraphLaunch calls in the region (b200tsdf_integrate_batch_device)                      */
+  int64_t nvlink_bytes;      /* bytes this rank received / sent over NCCL in the region (row all-gather, shard gather)     */
 } b200tsdf_profile;
 int  b200tsdf_profile_begin (b200tsdf_t* h);
 int  b200tsdf_profile_end (b200tsdf_t* h, b200tsdf_profile* out);
