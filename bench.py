@@ -270,7 +270,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     all_cpus = os.sched_getaffinity(0)
-    affinity = bind_to_gpu_numa(local_rank)
+    affinity = bind_to_gpu_numa(local_rank) if os.environ.get("B200TSDF_BIND_NUMA") == "1" else "default (unbound)"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -357,8 +357,9 @@ def main():
         with (HostLoad(os.cpu_count() or 1) if rank == 0 else contextlib.nullcontext()):
             step_device(k); k += FRAMES_PER_STEP
             vol.sync()
-            _, ms_loaded = timed(step_device, max(3, args.steps // 2))
-        host_load = {"value": max(3, args.steps // 2) * FRAMES_PER_STEP / (ms_loaded / 1e3), "unit": "frames/s",
+            n_loaded = max(16, args.steps)
+            _, ms_loaded = timed(step_device, n_loaded)
+        host_load = {"value": n_loaded * FRAMES_PER_STEP / (ms_loaded / 1e3), "unit": "frames/s", "steps": n_loaded,
                      "load": f"{os.cpu_count()} busy-loop processes (one per host core) during the batched device-resident leg"}
 
     # ---- end-to-end leg (host buffers, public API) ---------------------------------------------

@@ -39,6 +39,10 @@ struct FrameRec
   int pad_[2];
   unsigned long long kt[2];// [0] start of the brick kernel (ns), [1] end of its last block; zeroed by the record upload
 };
+// programmatic dependent launch: the hot kernels of a frame are launched with programmatic stream serialization, so the next
+// kernel's blocks become resident while this one drains and only wait (pdl_wait) before they touch what it wrote
+__device__ __forceinline__ void pdl_launch_dependents () { asm volatile ("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait () { asm volatile ("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long global_ns () { unsigned long long t; asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 constexpr int MAX_QLEVELS = 8;
@@ -1000,12 +1004,14 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
   __shared__ __align__ (16) TopSmem S;
   __shared__ Frame s_f_;
   const int tid = threadIdx.x, lane = tid & 31;
+  pdl_launch_dependents ();
   {
     const int* src_ = reinterpret_cast<const int*> (&fr->f); int* dst_ = reinterpret_cast<int*> (&s_f_);
     for (int w_ = tid; w_ < (int) (sizeof (Frame) / sizeof (int)); w_ += TOP_THREADS) dst_[w_] = src_[w_];
   }
   int* const cnt_ = d_count + 16 * fr->cset;
   __syncthreads ();
+  pdl_wait ();                                          // everything below reads what k_front wrote
   const Frame& f = s_f_;
   unsigned long long upd = 0, vis = 0;
   int count = cnt_[0];
@@ -1174,6 +1180,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
   __shared__ Frame sf_;
   __shared__ FreshRec s_rec[4][FRESH_RECS];          // per-warp records of the breadth-first re-split visit
   __shared__ int s_cnt[4];
+  pdl_launch_dependents ();
   {
     const int* s1 = reinterpret_cast<const int*> (&gp); int* d1 = reinterpret_cast<int*> (&sp_);
     for (int w = threadIdx.x; w < (int) (sizeof (Params) / sizeof (int)); w += blockDim.x) d1[w] = s1[w];
@@ -1181,6 +1188,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
     for (int w = threadIdx.x; w < (int) (sizeof (Frame) / sizeof (int)); w += blockDim.x) d2[w] = s2[w];
   }
   __syncthreads ();
+  pdl_wait ();
   const Params& p = sp_;
   const Frame& f = sf_;
   const int lane = threadIdx.x & 31;

@@ -38,6 +38,7 @@ struct Planes { float pl[6][4]; };
 enum StatSlot { ST_UPDATES = 0, ST_VISITS = 1, ST_BLOCKS = 2, ST_N = 8, ST_TOTAL = 2 * ST_N + 1, ST_SCRATCH = 2 * ST_N };
 constexpr int KRING = 64;     // ring of event pairs around the dominant kernel
 constexpr int FRAME_RING = 64;  // per-frame records in flight (device ring + its pinned host image)
+constexpr int BATCH_SEGS = 16;  // host staging segments of the batch path
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -100,7 +101,9 @@ __global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restr
 __global__ void k_front (Params p, const FrameRec* __restrict__ fr, int cull_blocks, int* __restrict__ list, int* __restrict__ d_count, QNode* __restrict__ q0,
                          unsigned long long* __restrict__ stats)
 {
+  pdl_launch_dependents ();
   B2_STAGE_FRAME (fr)
+  pdl_wait ();                                          // the previous frame's bottom-up sweep has finished
   int* count = d_count + 16 * s_fr_.cset;
   int* next_counts = d_count + 16 * (s_fr_.cset ^ 1);
   // frame-begin bookkeeping (was a launch of its own): snapshot the cumulative counters, and clear the counter
@@ -208,6 +211,15 @@ __global__ void k_list_bricks (Params p, int* __restrict__ list, int* __restrict
   size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i > p.pool_mask) return;
   if (p.keys[i] != KEY_EMPTY) list[atomicAdd (count, 1)] = (int) i;
+}
+
+// number of claimed directory slots (statistics): one atomic per warp
+__global__ void k_count_bricks (Params p, int* __restrict__ count)
+{
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const bool used = i <= p.pool_mask && p.keys[i] != KEY_EMPTY;
+  const unsigned m = __ballot_sync (0xffffffffu, used);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd (count, __popc (m));
 }
 
 __global__ void k_gather_bricks (Params p, const int* __restrict__ list, int n,
@@ -369,7 +381,7 @@ struct b200tsdf
   bool has_volume = false;
   Params p{};
   int device = 0, sm_count = 148;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, gather_stream = nullptr;   // compute | H2D uploads | pack + NVLink all-gather
   size_t pool = 0;
   bool alloc_color = false, alloc_var = false;
   size_t root_n = 0;
@@ -391,6 +403,7 @@ struct b200tsdf
   // fused per-cell upper sweeps (coarse cells are the top-tier roots and the block roots are <= 3 levels below)
   bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0; CellTop* d_celltop = nullptr; bool top_path = false;
   bool fast_path = false; int force_general = 0;
+  bool use_pdl = true;           // programmatic dependent launch between the hot kernels (B200TSDF_PDL=0 turns it off)
   int bd_minb = 6;               // resident CTAs per SM the brick kernel is compiled for (80 registers; tuning knob: B200TSDF_BD_MINB=6|8)
   // device copy of Params (the rare out-of-line paths read it through a pointer) and the ring of per-frame records
   Params* d_params = nullptr;
@@ -400,15 +413,18 @@ struct b200tsdf
   cudaEvent_t ev_ring[2] = { nullptr, nullptr };
   // batches (b200tsdf_integrate_batch_device): their own record ring, used half by half, and one captured graph per
   // (half, batch size); a graph is valid until the next reset()
-  FrameRec* d_bring = nullptr; FrameRec* h_bring = nullptr; int bring_half = 0; bool bring_used[2] = { false, false };
-  cudaEvent_t ev_bring[2] = { nullptr, nullptr };
+  // device slots: two halves of FRAME_RING / 2 records, reused in stream order; host staging: BATCH_SEGS segments written round
+  // robin — the host only waits when it is BATCH_SEGS batches ahead of the device
+  FrameRec* d_bring = nullptr; FrameRec* h_bring = nullptr; int bring_half = 0; int bring_seg = 0; bool bring_used[BATCH_SEGS] = {};
+  cudaEvent_t ev_bring[BATCH_SEGS] = {};
+  cudaEvent_t ev_half_done[2] = { nullptr, nullptr }; bool half_used[2] = { false, false }; FrameRec* batch_recs = nullptr;
   cudaGraphExec_t batch_exec[2][FRAME_RING / 2 + 1] = {};
   // multi-GPU (multigpu.cuh): NCCL communicator (opaque here), row-sliced uploads
   void* comm = nullptr; int comm_rank = 0, comm_size = 1;
   unsigned char* d_rows_raw[2] = { nullptr, nullptr }; unsigned char* d_rows_full[2] = { nullptr, nullptr };
   size_t rows_raw_cap = 0, rows_full_cap = 0; int rows_set = 0; bool rows_used[2] = { false, false };
-  int rows_chunk = 4;            // frames per upload/fuse pipeline stage of b200tsdf_integrate_batch_rows (B200TSDF_ROWS_CHUNK=2..32)
-  cudaEvent_t ev_rows_ready[2][16] = {}, ev_rows_done[2] = { nullptr, nullptr };
+  int rows_chunk = 8;            // frames per upload/fuse pipeline stage of b200tsdf_integrate_batch_rows (B200TSDF_ROWS_CHUNK=2..32)
+  cudaEvent_t ev_rows_up[2][16] = {}, ev_rows_ready[2][16] = {}, ev_rows_done[2] = { nullptr, nullptr };
   long long nvlink_bytes = 0, prof_nvlink0 = 0;
   int launches_per_frame = 0; long long graph_launches = 0, prof_graph0 = 0;
   // measurement
@@ -456,6 +472,19 @@ void free_volume (b200tsdf* h)
   h->p.keys = nullptr; h->p.nodes = nullptr; h->p.split = nullptr; h->p.rgb = nullptr; h->p.M = nullptr; h->p.ns = nullptr;
   h->p.root_dw = nullptr; h->p.root_split = nullptr; h->p.root_rgb = nullptr; h->p.root_M = nullptr; h->p.root_ns = nullptr;
   h->pool = 0; h->root_n = 0;
+}
+
+// launch with programmatic stream serialization (see pdl_wait in brick_kernels.cuh); also valid inside a stream capture
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl (void (*kernel) (KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx (&cfg, kernel, KArgs (args)...);
 }
 
 void comm_release (b200tsdf* h);          // multigpu.cuh
@@ -515,6 +544,7 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   b200tsdf* h = new b200tsdf;
   if (cfg) h->cfg_pending = *cfg; else b200tsdf_default_config (&h->cfg_pending);
   h->device = h->cfg_pending.device;
+  if (const char* e = std::getenv ("B200TSDF_PDL")) h->use_pdl = std::atoi (e) != 0;
   if (const char* e = std::getenv ("B200TSDF_ROWS_CHUNK")) { const int v = std::atoi (e); if (v >= 2 && v <= 32) h->rows_chunk = v; }
   if (const char* e = std::getenv ("B200TSDF_BD_MINB")) { const int v = std::atoi (e); if (v == 6 || v == 8) h->bd_minb = v; }
   if (h->device < 0 || h->device >= ndev) { delete h; return B200TSDF_EINVAL; }
@@ -522,6 +552,7 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
          && cudaDeviceGetAttribute (&h->sm_count, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess
          && cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking) == cudaSuccess
          && cudaStreamCreateWithFlags (&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess
+         && cudaStreamCreateWithFlags (&h->gather_stream, cudaStreamNonBlocking) == cudaSuccess
          && cudaMalloc (&h->d_err, sizeof (int)) == cudaSuccess
          && cudaMalloc (&h->d_count, 64 * sizeof (int)) == cudaSuccess
          && cudaMalloc (&h->d_stats, ST_TOTAL * sizeof (unsigned long long)) == cudaSuccess
@@ -532,18 +563,19 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
          && cudaEventCreateWithFlags (&h->ev_ring[0], cudaEventDisableTiming) == cudaSuccess
          && cudaEventCreateWithFlags (&h->ev_ring[1], cudaEventDisableTiming) == cudaSuccess
          && cudaMalloc (&h->d_bring, FRAME_RING * sizeof (FrameRec)) == cudaSuccess
-         && cudaHostAlloc (&h->h_bring, FRAME_RING * sizeof (FrameRec), cudaHostAllocDefault) == cudaSuccess
+         && cudaHostAlloc (&h->h_bring, (size_t) BATCH_SEGS * (FRAME_RING / 2) * sizeof (FrameRec), cudaHostAllocDefault) == cudaSuccess
          && cudaEventCreateWithFlags (&h->ev_rows_done[0], cudaEventDisableTiming) == cudaSuccess
-         && cudaEventCreateWithFlags (&h->ev_rows_done[1], cudaEventDisableTiming) == cudaSuccess
-         && cudaEventCreateWithFlags (&h->ev_bring[0], cudaEventDisableTiming) == cudaSuccess
-         && cudaEventCreateWithFlags (&h->ev_bring[1], cudaEventDisableTiming) == cudaSuccess;
+         && cudaEventCreateWithFlags (&h->ev_rows_done[1], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < BATCH_SEGS; ++i) ok = cudaEventCreateWithFlags (&h->ev_bring[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags (&h->ev_half_done[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i)
     ok = cudaEventCreateWithFlags (&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess
       && cudaEventCreateWithFlags (&h->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreate (&h->ev_t0) == cudaSuccess && cudaEventCreate (&h->ev_t1) == cudaSuccess
           && cudaEventCreate (&h->ev_k0) == cudaSuccess && cudaEventCreate (&h->ev_k1) == cudaSuccess
           && cudaEventCreate (&h->ev_p0) == cudaSuccess && cudaEventCreate (&h->ev_p1) == cudaSuccess;
-  for (int i = 0; ok && i < 32; ++i) ok = cudaEventCreateWithFlags (&h->ev_rows_ready[i / 16][i % 16], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 32; ++i) ok = cudaEventCreateWithFlags (&h->ev_rows_ready[i / 16][i % 16], cudaEventDisableTiming) == cudaSuccess
+                                          && cudaEventCreateWithFlags (&h->ev_rows_up[i / 16][i % 16], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < KRING; ++i)
     ok = cudaEventCreate (&h->kring[i][0]) == cudaSuccess && cudaEventCreate (&h->kring[i][1]) == cudaSuccess;
   if (ok) *h->h_err = 0;
@@ -561,6 +593,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   cudaSetDevice (h->device);
   if (h->stream) cudaStreamSynchronize (h->stream);
   if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
+  if (h->gather_stream) cudaStreamSynchronize (h->gather_stream);
   free_volume (h);
   cudaFree (h->d_err); cudaFree (h->d_count); cudaFree (h->d_stats); cudaFree (h->d_culled); cudaFree (h->d_scratch);
   cudaFree (h->d_dbg); if (h->h_err) cudaFreeHost (h->h_err);
@@ -571,11 +604,12 @@ void b200tsdf_destroy (b200tsdf_t* h)
   for (int i = 0; i < 2; ++i)
   {
     cudaFree (h->d_rows_raw[i]); cudaFree (h->d_rows_full[i]);
-    for (int k = 0; k < 16; ++k) if (h->ev_rows_ready[i][k]) cudaEventDestroy (h->ev_rows_ready[i][k]);
+    for (int k = 0; k < 16; ++k) { if (h->ev_rows_ready[i][k]) cudaEventDestroy (h->ev_rows_ready[i][k]); if (h->ev_rows_up[i][k]) cudaEventDestroy (h->ev_rows_up[i][k]); }
     if (h->ev_rows_done[i]) cudaEventDestroy (h->ev_rows_done[i]);
   }
   cudaFree (h->d_bring); if (h->h_bring) cudaFreeHost (h->h_bring);
-  for (int i = 0; i < 2; ++i) if (h->ev_bring[i]) cudaEventDestroy (h->ev_bring[i]);
+  for (int i = 0; i < BATCH_SEGS; ++i) if (h->ev_bring[i]) cudaEventDestroy (h->ev_bring[i]);
+  for (int i = 0; i < 2; ++i) if (h->ev_half_done[i]) cudaEventDestroy (h->ev_half_done[i]);
   cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
@@ -584,6 +618,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   for (int i = 0; i < KRING; ++i) { if (h->kring[i][0]) cudaEventDestroy (h->kring[i][0]); if (h->kring[i][1]) cudaEventDestroy (h->kring[i][1]); }
   if (h->stream) cudaStreamDestroy (h->stream);
   if (h->copy_stream) cudaStreamDestroy (h->copy_stream);
+  if (h->gather_stream) cudaStreamDestroy (h->gather_stream);
   std::free (h->mesh_v); std::free (h->mesh_c);
   delete h;
 }
@@ -621,7 +656,8 @@ int b200tsdf_reset (b200tsdf_t* h)
   CK (cudaStreamSynchronize (h->stream));
   CK (cudaStreamSynchronize (h->copy_stream));
   drop_batch_graphs (h);                                   // captured launches carry the old configuration
-  h->bring_used[0] = h->bring_used[1] = false;
+  for (int i = 0; i < BATCH_SEGS; ++i) h->bring_used[i] = false;
+  h->half_used[0] = h->half_used[1] = false;
   if (pool != h->pool || root_n != h->root_n || color != h->alloc_color || var != h->alloc_var)
   {
     h->has_volume = false;                                 // a failed allocation below must not leave a half-built volume usable
@@ -766,7 +802,9 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
   const int ncells = 1 << (3 * p.C);
   {
     const int cull_blocks = (ncells + 255) / 256;
-    k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, d_rec, cull_blocks, h->d_culled, h->d_count, h->fast_path ? h->Q.q[0] : nullptr, h->d_stats);
+    const bool pdl = h->top_path && h->use_pdl;
+    if (pdl) CK (launch_pdl (k_front, dim3 (cull_blocks + (npix + 255) / 256), dim3 (256), s, p, d_rec, cull_blocks, h->d_culled, h->d_count, h->Q.q[0], h->d_stats));
+    else k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, d_rec, cull_blocks, h->d_culled, h->d_count, h->fast_path ? h->Q.q[0] : nullptr, h->d_stats);
   }
   h->launches += 1;
   int kr = -1;
@@ -788,8 +826,9 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
       bli = NL;
       if (h->top_path)
       {
-        if (p.color) k_celltop_down<true><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats);
-        else k_celltop_down<false><<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats);
+        auto kd = p.color ? k_celltop_down<true> : k_celltop_down<false>;
+        if (h->use_pdl) CK (launch_pdl (kd, dim3 (h->sm_count * 4), dim3 (TOP_THREADS), s, p, d_rec, (const QNode*) h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats));
+        else kd<<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats);
       }
       else if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
       else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
@@ -801,15 +840,11 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][0], s));
     // the dominant kernel: one warp per interior block root, the brick updated in place
     (void) d_bailcount;
-    if (h->bd_minb == 6)
     {
-      if (p.color) k_bricks<true, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
-      else k_bricks<false, 6><<<h->sm_count * 6, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
-    }
-    else
-    {
-      if (p.color) k_bricks<true, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
-      else k_bricks<false, 8><<<h->sm_count * 8, BD_WARPS * 32, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
+      auto kb = h->bd_minb == 6 ? (p.color ? k_bricks<true, 6> : k_bricks<false, 6>) : (p.color ? k_bricks<true, 8> : k_bricks<false, 8>);
+      const dim3 g (h->sm_count * h->bd_minb), b (BD_WARPS * 32);
+      if (h->top_path && h->use_pdl) CK (launch_pdl (kb, g, b, s, p, (const Params*) h->d_params, d_rec, Qb.q[bli], (const int*) h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3));
+      else kb<<<g, b, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
     }
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
@@ -818,8 +853,9 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
       const int NL = h->cell_nl;
       if (h->top_path)
       {
-        if (p.color) k_celltop_up<true><<<h->sm_count, 128, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
-        else k_celltop_up<false><<<h->sm_count, 128, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
+        auto ku = p.color ? k_celltop_up<true> : k_celltop_up<false>;
+        if (h->use_pdl) CK (launch_pdl (ku, dim3 (h->sm_count), dim3 (128), s, p, d_rec, (const QNode*) h->Q.q[0], (const int*) h->d_count, (const QNode*) h->d_cellq, (const CellTop*) h->d_celltop, h->cell_cap, h->d_stats));
+        else ku<<<h->sm_count, 128, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
       }
       else if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
       else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
@@ -903,6 +939,64 @@ int b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t strid
 }
 
 // a batch of frames resident in device memory: one upload of the frame records, one graph launch
+// The two halves of a batch: (1) the frame records are written into a host staging segment and uploaded on `rec_stream`
+// into one half of the device slots; (2) the captured launches of that half are replayed on the compute stream.  The row
+// path (multigpu.cuh) uploads the records on its copy stream AHEAD of the frames themselves — a record upload issued on
+// the compute stream would queue behind every frame copy already submitted to the one host-to-device copy engine.
+static int batch_records (b200tsdf* h, int m, const void* const* d_points, size_t stride, int xyz_off, int rgba_off, int width, int height,
+                          const double* poses_c2w, cudaStream_t rec_stream)
+{
+  constexpr int HALF = FRAME_RING / 2;
+  const int a = h->bring_half, sg = h->bring_seg;
+  if (h->bring_used[sg]) CK (cudaEventSynchronize (h->ev_bring[sg]));    // the copy that last read this staging segment has run
+  FrameRec* recs = h->h_bring + (size_t) sg * HALF;
+  for (int i = 0; i < m; ++i)
+  {
+    if (!d_points[i]) return h->fail (B200TSDF_EINVAL, "null cloud in batch");
+    fill_rec (h, recs[i], (const unsigned char*) d_points[i], stride, xyz_off, rgba_off, width, height, poses_c2w + 16 * (size_t) i);
+  }
+  // the device half is rewritten only after the launches that last read it (other stream: wait for their event)
+  if (rec_stream != h->stream && h->half_used[a]) CK (cudaStreamWaitEvent (rec_stream, h->ev_half_done[a], 0));
+  CK (cudaMemcpyAsync (h->d_bring + a * HALF, recs, (size_t) m * sizeof (FrameRec), cudaMemcpyHostToDevice, rec_stream));
+  CK (cudaEventRecord (h->ev_bring[sg], rec_stream));      // the staging segment is free again once this copy has run
+  h->bring_used[sg] = true; h->bring_seg = (sg + 1) % BATCH_SEGS;
+  h->batch_recs = recs;
+  return B200TSDF_OK;
+}
+static int batch_launch (b200tsdf* h, int m)
+{
+  constexpr int HALF = FRAME_RING / 2;
+  cudaStream_t s = h->stream;
+  const int a = h->bring_half;
+  cudaGraphExec_t& exec = h->batch_exec[a][m];          // (nothing of a frame is baked into the launches: they read the record)
+  if (!exec)
+  {
+    const long long l0 = h->launches, f0 = h->prof_frames;
+    cudaGraph_t g = nullptr;
+    CK (cudaStreamBeginCapture (s, cudaStreamCaptureModeThreadLocal));
+    int rc = B200TSDF_OK;
+    for (int i = 0; i < m && rc == B200TSDF_OK; ++i) rc = launch_frame (h, s, h->batch_recs[i], h->d_bring + a * HALF + i, false);
+    cudaError_t ce = cudaStreamEndCapture (s, &g);
+    h->launches_per_frame = (int) ((h->launches - l0) / std::max (1, m));
+    h->launches = l0; h->prof_frames = f0;
+    if (rc) { if (g) cudaGraphDestroy (g); return rc; }
+    if (ce != cudaSuccess) return h->fail (B200TSDF_ECUDA, std::string ("graph capture: ") + cudaGetErrorString (ce));
+    ce = cudaGraphInstantiate (&exec, g, 0);
+    cudaGraphDestroy (g);
+    if (ce != cudaSuccess) { exec = nullptr; return h->fail (B200TSDF_ECUDA, std::string ("graph instantiate: ") + cudaGetErrorString (ce)); }
+  }
+  CK (cudaGraphLaunch (exec, s));
+  CK (cudaEventRecord (h->ev_half_done[a], s));
+  h->half_used[a] = true;
+  note_device_err (h, s);
+  h->bring_half ^= 1;
+  h->launches += (long long) m * h->launches_per_frame; h->graph_launches++;
+  h->prof_frames += m;
+  h->timed = false;
+  h->is_empty = false;
+  return B200TSDF_OK;
+}
+
 int b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_points, size_t stride, int xyz_off, int rgba_off,
                                      int width, int height, const double* poses_c2w)
 {
@@ -912,7 +1006,6 @@ int b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_
   cudaSetDevice (h->device);
   if (int rc = pending_device_err (h)) return rc;
   constexpr int HALF = FRAME_RING / 2;
-  cudaStream_t s = h->stream;
   for (int done = 0; done < n;)
   {
     const int m = std::min (HALF, n - done);
@@ -924,42 +1017,10 @@ int b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_
       done += m;
       continue;
     }
-    const int a = h->bring_half;
-    if (h->bring_used[a]) CK (cudaEventSynchronize (h->ev_bring[a]));      // the copy that last read this half of the host image has run
-    FrameRec* recs = h->h_bring + a * HALF;
-    for (int i = 0; i < m; ++i)
-    {
-      if (!d_points[done + i]) return h->fail (B200TSDF_EINVAL, "null cloud in batch");
-      fill_rec (h, recs[i], (const unsigned char*) d_points[done + i], stride, xyz_off, rgba_off, width, height, poses_c2w + 16 * (size_t) (done + i));
-    }
-    cudaGraphExec_t& exec = h->batch_exec[a][m];          // (nothing of a frame is baked into the launches: they read the record)
-    CK (cudaMemcpyAsync (h->d_bring + a * HALF, recs, (size_t) m * sizeof (FrameRec), cudaMemcpyHostToDevice, s));
-    if (!exec)
-    {
-      const long long l0 = h->launches, f0 = h->prof_frames;
-      cudaGraph_t g = nullptr;
-      CK (cudaStreamBeginCapture (s, cudaStreamCaptureModeThreadLocal));
-      int rc = B200TSDF_OK;
-      for (int i = 0; i < m && rc == B200TSDF_OK; ++i) rc = launch_frame (h, s, recs[i], h->d_bring + a * HALF + i, false);
-      cudaError_t ce = cudaStreamEndCapture (s, &g);
-      h->launches_per_frame = (int) ((h->launches - l0) / std::max (1, m));
-      h->launches = l0; h->prof_frames = f0;
-      if (rc) { if (g) cudaGraphDestroy (g); return rc; }
-      if (ce != cudaSuccess) return h->fail (B200TSDF_ECUDA, std::string ("graph capture: ") + cudaGetErrorString (ce));
-      ce = cudaGraphInstantiate (&exec, g, 0);
-      cudaGraphDestroy (g);
-      if (ce != cudaSuccess) { exec = nullptr; return h->fail (B200TSDF_ECUDA, std::string ("graph instantiate: ") + cudaGetErrorString (ce)); }
-    }
-    CK (cudaGraphLaunch (exec, s));
-    note_device_err (h, s);
-    CK (cudaEventRecord (h->ev_bring[a], s));
-    h->bring_used[a] = true; h->bring_half ^= 1;
-    h->launches += (long long) m * h->launches_per_frame; h->graph_launches++;
-    h->prof_frames += m;
+    if (int rc = batch_records (h, m, d_points + done, stride, xyz_off, rgba_off, width, height, poses_c2w + 16 * (size_t) done, h->stream)) return rc;
+    if (int rc = batch_launch (h, m)) return rc;
     done += m;
   }
-  h->timed = false;
-  if (n) h->is_empty = false;
   CK (cudaGetLastError ());
   return B200TSDF_OK;
 }
@@ -1086,6 +1147,7 @@ int b200tsdf_sync (b200tsdf_t* h)
   if (!h) return B200TSDF_EINVAL;
   cudaSetDevice (h->device);
   CK (cudaStreamSynchronize (h->copy_stream));
+  CK (cudaStreamSynchronize (h->gather_stream));
   return check_device_err (h);
 }
 
@@ -1109,16 +1171,13 @@ int b200tsdf_get_stats (b200tsdf_t* h, b200tsdf_stats* s)
   s->n_culled_cells = cnt[0];
   s->pool_capacity = (int64_t) h->pool;
   s->coarse_level = h->p.C; s->finest_level = h->p.L; s->tiers = h->p.T;
-  // allocated bricks
+  // allocated bricks (no allocation, no list: this call sits in measured loops)
   int* d_n = h->d_count + 40;
-  CK (cudaMemset (d_n, 0, sizeof (int)));
-  int* d_list = nullptr;
-  CK (cudaMalloc (&d_list, h->pool * sizeof (int)));
-  k_list_bricks<<<(unsigned) ((h->pool + 255) / 256), 256, 0, h->stream>>> (h->p, d_list, d_n);
+  CK (cudaMemsetAsync (d_n, 0, sizeof (int), h->stream));
+  k_count_bricks<<<(unsigned) ((h->pool + 255) / 256), 256, 0, h->stream>>> (h->p, d_n);
   int nb = 0;
-  cudaMemcpyAsync (&nb, d_n, sizeof (int), cudaMemcpyDeviceToHost, h->stream);
-  cudaStreamSynchronize (h->stream);
-  cudaFree (d_list);
+  CK (cudaMemcpyAsync (&nb, d_n, sizeof (int), cudaMemcpyDeviceToHost, h->stream));
+  CK (cudaStreamSynchronize (h->stream));
   s->n_bricks = nb;
   if (h->timed)
   {

@@ -174,42 +174,58 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
     }
     h->rows_raw_cap = need_raw; h->rows_full_cap = need_full;
   }
-  cudaStream_t cs = h->copy_stream;
-  if (h->rows_used[s]) CK (cudaStreamWaitEvent (cs, h->ev_rows_done[s], 0));
-  // chunks of ROWS_CHUNK frames: while chunk c is being fused, chunk c + 1 crosses PCIe / NVLink on the copy stream
+  // three-stage pipeline, ROWS_CHUNK frames per stage: the copy stream only uploads (the copy engine never waits for a
+  // kernel), the gather stream packs and all-gathers, the compute stream fuses.  Grid shapes without replayable launches
+  // are fused frame by frame once their chunk has arrived.
+  cudaStream_t cs = h->copy_stream, gs = h->gather_stream;
+  if (int rc = pending_device_err (h)) return rc;
+  if (h->rows_used[s]) { CK (cudaStreamWaitEvent (cs, h->ev_rows_done[s], 0)); CK (cudaStreamWaitEvent (gs, h->ev_rows_done[s], 0)); }
+  const int npts = (row1 - row0) * width;
+  const int out_rgba = (h->p.color && rgba_off >= 0) ? 12 : -1;
   for (int c0 = 0; c0 < n; c0 += ROWS_CHUNK)
   {
     const int m = std::min (ROWS_CHUNK, n - c0);
+    const void* ptrs[HALF];
+    for (int i = 0; i < m; ++i)
+      ptrs[i] = nr == 1 ? (const void*) (h->d_rows_raw[s] + (size_t) (c0 + i) * per * width * stride)      // one rank: fused where it landed
+                        : (const void*) (h->d_rows_full[s] + (size_t) (c0 + i) * frame16);
+    const size_t f_stride = nr == 1 ? stride : 16; const int f_xyz = nr == 1 ? xyz_off : 0, f_rgba = nr == 1 ? rgba_off : out_rgba;
+    // the chunk's frame records travel on the copy stream ahead of its frames
+    if (h->top_path) { if (int rc = batch_records (h, m, ptrs, f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) c0, cs)) return rc; }
     for (int i = c0; i < c0 + m; ++i)
     {
       if (!rows[i] && slice_raw) return h->fail (B200TSDF_EINVAL, "null row slice in batch");
-      unsigned char* raw = h->d_rows_raw[s] + (size_t) i * per * width * stride;
-      if (slice_raw) CK (cudaMemcpyAsync (raw, rows[i], slice_raw, cudaMemcpyHostToDevice, cs));
+      if (slice_raw) CK (cudaMemcpyAsync (h->d_rows_raw[s] + (size_t) i * per * width * stride, rows[i], slice_raw, cudaMemcpyHostToDevice, cs));
       h->h2d_bytes += (long long) slice_raw;
-      const int npts = (row1 - row0) * width;
-      uint4* dst = reinterpret_cast<uint4*> (h->d_rows_full[s] + (size_t) i * frame16 + (size_t) rk * slice16);
-      if (npts) k_pack_rows<<<(npts + 255) / 256, 256, 0, cs>>> (raw, stride, xyz_off, h->p.color ? rgba_off : -1, npts, dst);
     }
-    h->launches += m;
+    cudaEvent_t up = h->ev_rows_up[s][c0 / ROWS_CHUNK], ready = up;
+    CK (cudaEventRecord (up, cs));
     if (nr > 1)
     {
+      CK (cudaStreamWaitEvent (gs, up, 0));
+      for (int i = c0; i < c0 + m && npts; ++i)
+      {
+        uint4* dst = reinterpret_cast<uint4*> (h->d_rows_full[s] + (size_t) i * frame16 + (size_t) rk * slice16);
+        k_pack_rows<<<(npts + 255) / 256, 256, 0, gs>>> (h->d_rows_raw[s] + (size_t) i * per * width * stride, stride, xyz_off, h->p.color ? rgba_off : -1, npts, dst);
+      }
+      h->launches += m;
       // one grouped launch: m in-place all-gathers, frame i's slices land row-major in its full 16-byte image
       NK (a.GroupStart ());
       for (int i = c0; i < c0 + m; ++i)
       {
         unsigned char* full = h->d_rows_full[s] + (size_t) i * frame16;
-        NK (a.AllGather (full + (size_t) rk * slice16, full, slice16, ncclChar, (ncclComm_t) h->comm, cs));
+        NK (a.AllGather (full + (size_t) rk * slice16, full, slice16, ncclChar, (ncclComm_t) h->comm, gs));
       }
       NK (a.GroupEnd ());
       h->nvlink_bytes += (long long) m * (long long) slice16 * (nr - 1);
+      ready = h->ev_rows_ready[s][c0 / ROWS_CHUNK];
+      CK (cudaEventRecord (ready, gs));
     }
-    cudaEvent_t ready = h->ev_rows_ready[s][c0 / ROWS_CHUNK];
-    CK (cudaEventRecord (ready, cs));
     CK (cudaStreamWaitEvent (h->stream, ready, 0));
-    const void* ptrs[HALF];
-    for (int i = 0; i < m; ++i) ptrs[i] = h->d_rows_full[s] + (size_t) (c0 + i) * frame16;
-    int rc = b200tsdf_integrate_batch_device (h, m, ptrs, 16, 0, (h->p.color && rgba_off >= 0) ? 12 : -1, width, height, poses_c2w + 16 * (size_t) c0);
-    if (rc) return rc;
+    if (h->top_path) { if (int rc = batch_launch (h, m)) return rc; }
+    else
+      for (int i = 0; i < m; ++i)
+        if (int rc = integrate_on_device (h, (const unsigned char*) ptrs[i], f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) (c0 + i))) return rc;
   }
   CK (cudaEventRecord (h->ev_rows_done[s], h->stream));
   h->rows_used[s] = true; h->rows_set ^= 1;
