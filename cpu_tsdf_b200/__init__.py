@@ -72,7 +72,7 @@ EXPORTS = [
     "b200tsdf_default_config", "b200tsdf_create", "b200tsdf_destroy", "b200tsdf_last_error",
     "b200tsdf_set_config", "b200tsdf_get_config", "b200tsdf_reset", "b200tsdf_integrate",
     "b200tsdf_integrate_device", "b200tsdf_integrate_batch_device", "b200tsdf_integrate_async",
-    "b200tsdf_comm_unique_id", "b200tsdf_comm_init", "b200tsdf_row_slice", "b200tsdf_integrate_batch_rows", "b200tsdf_gather_volume", "b200tsdf_sync", "b200tsdf_organize", "b200tsdf_integrate_unorganized", "b200tsdf_query", "b200tsdf_render", "b200tsdf_mesh",
+    "b200tsdf_comm_unique_id", "b200tsdf_comm_init", "b200tsdf_row_slice", "b200tsdf_integrate_batch_rows", "b200tsdf_gather_volume", "b200tsdf_sync", "b200tsdf_organize", "b200tsdf_integrate_unorganized", "b200tsdf_query", "b200tsdf_interpolate", "b200tsdf_render", "b200tsdf_mesh",
     "b200tsdf_free", "b200tsdf_save", "b200tsdf_load", "b200tsdf_export_shard", "b200tsdf_import_shard", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
     "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_frustum_cull",
     "b200tsdf_profile_begin", "b200tsdf_profile_end",
@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
     lib.b200tsdf_organize.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(OrganizeOpts), vp, C.c_size_t, C.c_int, C.POINTER(C.c_int64)]
     lib.b200tsdf_integrate_unorganized.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(OrganizeOpts), vp]
     lib.b200tsdf_query.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.b200tsdf_interpolate.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.b200tsdf_render.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, vp]
     lib.b200tsdf_mesh.argtypes = [vp, C.c_float, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.b200tsdf_save.argtypes = [vp, C.c_char_p]
@@ -360,6 +361,17 @@ class TSDFVolumeOctree:
         hess = np.full((n, 3, 3), np.nan, np.float32); ok = np.zeros(n, np.uint8)
         self._check(self._lib.b200tsdf_query(self._h, _ptr(xyz), n, what, mode, _ptr(val), _ptr(grad), _ptr(hess), _ptr(ok)))
         return val, grad, hess, ok.astype(bool)
+
+    def getTSDFValue(self, pts, valid_in=True):
+        """getTSDFValue / interpolateTrilinearly (cpp:454-541), batched: returns (values, valid); `valid` starts as valid_in and is
+        only ever cleared, like the reference's `bool* valid`."""
+        xyz = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+        n = len(xyz)
+        val = np.zeros(n, np.float32); ok = np.full(n, 1 if valid_in else 0, np.uint8)
+        self._check(self._lib.b200tsdf_interpolate(self._h, _ptr(xyz), n, _ptr(val), _ptr(ok)))
+        return val, ok.astype(bool)
+
+    interpolateTrilinearly = getTSDFValue
 
     def getFxn(self, pt):
         """cpp:655-672 — returns (ok, val); batched when pt is [N,3]."""

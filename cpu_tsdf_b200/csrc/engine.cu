@@ -192,6 +192,17 @@ __global__ void k_query (Params gp, const float* __restrict__ xyz, int n, int wh
   if (what & 4) for (int k = 0; k < 9; ++k) hess[9 * i + k] = hs[k];
 }
 
+// getTSDFValue = interpolateTrilinearly (tsdf_volume_octree.cpp:454-541), one thread per point
+__global__ void k_interpolate (Params gp, const float* __restrict__ xyz, int n, float* __restrict__ val, unsigned char* __restrict__ valid)
+{
+  B2_STAGE_PARAMS (gp)
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool v = valid[i] != 0;
+  val[i] = interpolate_trilinearly (p, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &v);
+  valid[i] = v ? 1 : 0;
+}
+
 __global__ void k_render (Params gp, RenderParams r, float* __restrict__ out /* 6 floats per pixel */, unsigned char* __restrict__ rgb)
 {
   B2_STAGE_PARAMS (gp)
@@ -1212,6 +1223,28 @@ int b200tsdf_query (b200tsdf_t* h, const float* xyz, int n, int what, int mode,
   if (what & 1) CK (cudaMemcpyAsync (val, d_val, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
   if (what & 2) CK (cudaMemcpyAsync (grad, d_grad, (size_t) n * 12, cudaMemcpyDeviceToHost, s));
   if (what & 4) CK (cudaMemcpyAsync (hess, d_hess, (size_t) n * 36, cudaMemcpyDeviceToHost, s));
+  note_device_err (h, s);
+  CK (cudaStreamSynchronize (s));
+  return pending_device_err (h);
+}
+
+// ---- getTSDFValue / interpolateTrilinearly (tsdf_volume_octree.cpp:454-541) ---------------------------------
+int b200tsdf_interpolate (b200tsdf_t* h, const float* xyz, int n, float* val, uint8_t* valid_in_out)
+{
+  if (!h || !xyz || !val || !valid_in_out || n < 0) return B200TSDF_EINVAL;
+  if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "getTSDFValue before reset()");
+  if (n == 0) return B200TSDF_OK;
+  cudaSetDevice (h->device);
+  { int rc = h->scratch ((size_t) n * 17 + 64); if (rc) return rc; }
+  float* d_xyz = (float*) h->d_scratch;
+  float* d_val = d_xyz + (size_t) 3 * n;
+  unsigned char* d_ok = (unsigned char*) (d_val + n);
+  cudaStream_t s = h->stream;
+  CK (cudaMemcpyAsync (d_xyz, xyz, (size_t) n * 12, cudaMemcpyHostToDevice, s));
+  CK (cudaMemcpyAsync (d_ok, valid_in_out, (size_t) n, cudaMemcpyHostToDevice, s));
+  k_interpolate<<<(n + 127) / 128, 128, 0, s>>> (h->p, d_xyz, n, d_val, d_ok);
+  CK (cudaMemcpyAsync (val, d_val, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+  CK (cudaMemcpyAsync (valid_in_out, d_ok, (size_t) n, cudaMemcpyDeviceToHost, s));
   note_device_err (h, s);
   CK (cudaStreamSynchronize (s));
   return pending_device_err (h);

@@ -129,6 +129,12 @@ int  b200tsdf_integrate_unorganized (b200tsdf_t* h, const void* points, size_t n
 int  b200tsdf_query (b200tsdf_t* h, const float* xyz, int n, int what, int mode,
                      float* val, float* grad, float* hess, uint8_t* ok);
 
+/* getTSDFValue (cpp:454-478) = interpolateTrilinearly (cpp:486-541; use_trilinear_interpolation_ is always true, cpp:80):
+ * the trilinear blend of the eight voxels around each point.  val[i] is NaN when the point's voxel is outside the volume or on
+ * its border layer; valid_in_out[i] is the caller's `*valid` on entry and is only ever cleared (border, or a neighbour with
+ * weight 0), exactly like the reference's pointer argument.  Host pointers. */
+int  b200tsdf_interpolate (b200tsdf_t* h, const float* xyz, int n, float* val, uint8_t* valid_in_out);
+
 /* renderView (cpp:278-424) and, with rgb_out != NULL, renderColoredView (cpp:427-450).
  * out: (W/ds)*(H/ds) points of `stride` bytes; xyz at xyz_off, normal at normal_off
  * (pcl::PointNormal: 0 / 16 / 48).  Camera frame, NaN xyz = miss. */

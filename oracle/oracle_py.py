@@ -67,6 +67,7 @@ def load(kind: str = "port") -> C.CDLL:
     lib.orc_integrate.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.orc_get_stats.argtypes = [vp, C.POINTER(OrcStats)]
     lib.orc_query.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.orc_interpolate.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.orc_render.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, vp]
     lib.orc_mesh.argtypes = [vp, C.c_float, C.c_int, C.POINTER(vp), C.POINTER(vp)]; lib.orc_mesh.restype = C.c_int64
     lib.orc_save.argtypes = [vp, C.c_char_p]
@@ -156,6 +157,14 @@ class OracleVolume:
         hess = np.full((n, 3, 3), np.nan, np.float32); ok = np.zeros(n, np.uint8)
         self.lib.orc_query(self.h, _ptr(xyz), n, what, mode, _ptr(val), _ptr(grad), _ptr(hess), _ptr(ok))
         return val, grad, hess, ok.astype(bool)
+
+    def interpolate(self, xyz: np.ndarray, valid_in=True):
+        """getTSDFValue = interpolateTrilinearly (cpp:454-541).  Returns (values, valid) with valid starting as `valid_in`."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        n = len(xyz)
+        val = np.zeros(n, np.float32); ok = np.full(n, 1 if valid_in else 0, np.uint8)
+        self.lib.orc_interpolate(self.h, _ptr(xyz), n, _ptr(val), _ptr(ok))
+        return val, ok.astype(bool)
 
     def render(self, pose: np.ndarray, downsample: int = 1, colored: bool = False):
         W, H = self.cfg.image_width // downsample, self.cfg.image_height // downsample

@@ -157,6 +157,20 @@ int orc_query (const orc_volume* v, const float* xyz, int n, int what, int mode,
   return 0;
 }
 
+// getTSDFValue / interpolateTrilinearly are protected: reach them through a derived class that republishes the names
+namespace { struct TsdfAccess : cpu_tsdf::TSDFVolumeOctree { using cpu_tsdf::TSDFVolumeOctree::getTSDFValue; }; }
+int orc_interpolate (const orc_volume* v, const float* xyz, int n, float* val, uint8_t* valid_in_out)
+{
+  const TsdfAccess& t = *static_cast<const TsdfAccess*> (v->tsdf.get ());
+  for (int i = 0; i < n; ++i)
+  {
+    bool valid = valid_in_out[i] != 0;
+    val[i] = t.getTSDFValue (xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &valid);
+    valid_in_out[i] = valid;
+  }
+  return 0;
+}
+
 int orc_render (const orc_volume* v, const double* pose, int downsample, void* out, size_t stride, int xyz_off, int normal_off, uint8_t* rgb_out)
 {
   uint8_t* base = static_cast<uint8_t*> (out);

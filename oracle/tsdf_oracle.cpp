@@ -577,6 +577,18 @@ int orc_query (const orc_volume* v, const float* xyz, int n, int what, int mode,
   return 0;
 }
 
+// ---- interpolateTrilinearly through getTSDFValue (use_trilinear_interpolation_ is true and has no setter, cpp:80, :454-541) ----
+int orc_interpolate (const orc_volume* v, const float* xyz, int n, float* val, uint8_t* valid_in_out)
+{
+  for (int i = 0; i < n; ++i)
+  {
+    bool valid = valid_in_out[i] != 0;
+    val[i] = v->interpolate_trilinearly (xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &valid);
+    valid_in_out[i] = valid;
+  }
+  return 0;
+}
+
 // ---- renderView, tsdf_volume_octree.cpp:278-424 (+ renderColoredView :427-450) -------------
 int orc_render (const orc_volume* v, const double* pose, int downsampleBy, void* out, size_t stride,
                 int xyz_off, int normal_off, uint8_t* rgb_out)

@@ -72,6 +72,9 @@ int  orc_query (const orc_volume* v, const float* xyz, int n, int what, int mode
 /* renderView (cpp:278-424): out = (W/ds)*(H/ds) points of `stride` bytes, xyz floats at
  * xyz_off, normal at normal_off (PointNormal: 0 / 16 / stride 48).  rgb_out (optional,
  * 3 bytes r,g,b per pixel) follows renderColoredView (cpp:427-450). */
+/* interpolateTrilinearly / getTSDFValue (tsdf_volume_octree.cpp:454-541; protected in the reference, reached through a derived
+ * accessor in the verbatim build): valid_in_out[i] is the caller's `*valid` on entry (the reference only ever clears it) */
+int  orc_interpolate (const orc_volume* v, const float* xyz, int n, float* val, uint8_t* valid_in_out);
 int  orc_render (const orc_volume* v, const double* pose, int downsample, void* out, size_t stride,
                  int xyz_off, int normal_off, uint8_t* rgb_out);
 

@@ -285,24 +285,21 @@ def _engine_2048(general=False, pool_log2=18):
 
 
 def test_full_size_stream_properties_2048(tmp_path):
-    # BASELINE.json's full size (640x480 into 2048^3, colour) is too slow for the CPU oracle over a long stream, so the
-    # 40-frame stream is checked through size-independent properties: (1) the fast brick-parallel path and the general
-    # depth-first path (a literal transcription of updateVoxel) agree bit for bit, (2) stored values stay in the
-    # reference's ranges, (3) save -> load -> save is the identity on bytes.
-    fast, slow = _engine_2048(False), _engine_2048(True)
+    # BASELINE.json's full size (640x480 into 2048^3, colour).  The 100-frame stream is compared with the reference itself in
+    # tests/test_golden.py (digests from oracle/_ref: nodes at 50 / 100 frames, renderView, marching cubes at w_min 2 and 0);
+    # here a 40-frame stream is checked through size-independent properties: stored values stay in the reference's ranges,
+    # save -> load -> save is the identity on bytes, and the reloaded volume renders identically.
+    fast = _engine_2048(False)
     upd = 0
     for f in range(40):
         pose = synth.orbit_pose(synth.S2, f, 100)
         cloud = synth.make_frame(synth.S2, pose, CAM, color=True, noise_seed=77, frame=f)
         fast.integrateCloud(cloud, None, pose)
-        slow.integrateCloud(cloud, None, pose)
         if f % 13 == 0:
-            assert fast.stats().n_updates == slow.stats().n_updates
             upd += fast.stats().n_updates
     assert upd > 1_000_000
-    a, b = fast.download_nodes(), slow.download_nodes()
+    a = fast.download_nodes()
     assert len(a["keys"]) > 2_000_000
-    assert_same_nodes(a, b, rgb=True)
     d, w = a["dw"][:, 0], a["dw"][:, 1]
     assert w.min() >= 0 and w.max() <= 100.0 and d.min() >= -1.0 and d.max() <= 1.0       # octree.cpp:156-159, hpp:189-198
     assert ((w == 0) <= (d == -1.0)).all()                                                  # never-observed nodes keep the constructor state
@@ -384,3 +381,20 @@ def test_batch_graph_replay_matches_the_oracle_and_frame_by_frame():
     e2.integrateBatchDevice([d.data_ptr() for d in dev2], H, W, 4 * fs2[0][1].shape[2], [p for p, _ in fs2])
     e2.sync()
     assert_same_nodes(o2.dump_nodes(), e2.download_nodes())
+
+
+def test_get_tsdf_value_direct_entry_point():
+    """b200tsdf_interpolate = getTSDFValue / interpolateTrilinearly (cpp:454-541): value bits, NaN on the border layer and outside,
+    and the in/out `valid` flag, against the oracle (itself pinned to the reference for this call in tests/test_ref_pin.py)."""
+    from tests.test_ref_pin import _interp_points
+    o, e = pair(CFG_256)
+    for pose, cloud in frames(synth.S1, 3, stride=9, noise_seed=5):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    pts = _interp_points()
+    for vin in (True, False):
+        va, oa = o.interpolate(pts, vin); vb, ob = e.getTSDFValue(pts, vin)
+        assert np.array_equal(oa, ob)
+        assert np.array_equal(np.isnan(va), np.isnan(vb))            # (the payload bits of a NaN are not part of the contract)
+        fin = ~np.isnan(va)
+        assert np.array_equal(va[fin].view(np.uint32), vb[fin].view(np.uint32))
+    assert e.getTSDFValue(pts, True)[1].sum() > 500
