@@ -49,6 +49,28 @@ def build(ref: bool = False) -> str:
 _libs: dict[str, C.CDLL] = {}
 
 
+REFPROG_LIB = os.path.join(HERE, "_ref", "libcpu_tsdf_refprog.so")
+
+
+def load_prog(kind: str = "port") -> C.CDLL:
+    """The program-side functions (organise / flattenVertices / cleanupMesh): "port" = oracle/prog_oracle.cpp inside the restatement
+    library, "reference" = the reference's own text of src/prog/integrate.cpp (oracle/_ref/libcpu_tsdf_refprog.so, `make refprog`)."""
+    if kind == "port":
+        return load("port")
+    if "refprog" in _libs:
+        return _libs["refprog"]
+    if not os.path.exists(REFPROG_LIB):
+        raise FileNotFoundError(REFPROG_LIB)
+    lib = C.CDLL(REFPROG_LIB)
+    vp = C.c_void_p
+    lib.orc_organize.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
+    lib.orc_organize.restype = C.c_int64
+    lib.orc_flatten_vertices.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_float, vp, vp, vp, vp]
+    lib.orc_cleanup_mesh.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_float, C.c_int, vp, vp, vp, vp]
+    _libs["refprog"] = lib
+    return lib
+
+
 def load(kind: str = "port") -> C.CDLL:
     """kind = "port" (the restatement) or "reference" (the reference's own sources, oracle/_ref)."""
     if kind in _libs:
@@ -87,10 +109,10 @@ def load(kind: str = "port") -> C.CDLL:
 
 
 def organize(points: np.ndarray, intr, width: int, height: int, *, rgba_off: int = -1, cloud_units: float = 1.0,
-             zero_nans: bool = False, world_to_camera=None):
+             zero_nans: bool = False, world_to_camera=None, kind: str = "port"):
     """integrate.cpp:548-607 — z-buffer an unorganised cloud ([n, k] float32 rows, xyz first, colour bytes at
     rgba_off) into [height, width, 8] float32 rows in pcl::PointXYZRGBA layout.  Returns (organized, n_filled)."""
-    lib = load("port")
+    lib = load_prog(kind)
     pts = np.ascontiguousarray(points, dtype=np.float32)
     intr = np.asarray(intr, np.float32)
     out = np.zeros((height, width, 8), np.float32)
@@ -228,11 +250,11 @@ def _mesh_call(fn, verts, tris, *args):
     return ov[:nv.value].copy(), ot[:nt.value].copy()
 
 
-def flatten_vertices(verts, tris, min_dist=0.0001):
+def flatten_vertices(verts, tris, min_dist=0.0001, kind: str = "port"):
     """flattenVertices, integrate.cpp:103-150 -> (vertices [n,3], triangles [m,3])"""
-    return _mesh_call(load("port").orc_flatten_vertices, verts, tris, C.c_float(min_dist))
+    return _mesh_call(load_prog(kind).orc_flatten_vertices, verts, tris, C.c_float(min_dist))
 
 
-def cleanup_mesh(verts, tris, face_dist=0.02, min_neighbors=5):
+def cleanup_mesh(verts, tris, face_dist=0.02, min_neighbors=5, kind: str = "port"):
     """cleanupMesh, integrate.cpp:152-214"""
-    return _mesh_call(load("port").orc_cleanup_mesh, verts, tris, C.c_float(face_dist), int(min_neighbors))
+    return _mesh_call(load_prog(kind).orc_cleanup_mesh, verts, tris, C.c_float(face_dist), int(min_neighbors))
