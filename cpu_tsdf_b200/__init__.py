@@ -38,7 +38,7 @@ class Config(C.Structure):
         ("integrate_color", C.c_int32), ("track_variance", C.c_int32),
         ("device", C.c_int32), ("pool_log2", C.c_int32),
         ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("debug_flags", C.c_int32), ("color_mode", C.c_int32), ("reserved", C.c_int32 * 2),
         ("global_transform", C.c_double * 16),
     ]
 
@@ -74,7 +74,7 @@ EXPORTS = [
     "b200tsdf_integrate_device", "b200tsdf_integrate_batch_device", "b200tsdf_integrate_async",
     "b200tsdf_comm_unique_id", "b200tsdf_comm_init", "b200tsdf_row_slice", "b200tsdf_integrate_batch_rows", "b200tsdf_gather_volume", "b200tsdf_sync", "b200tsdf_organize", "b200tsdf_integrate_unorganized", "b200tsdf_query", "b200tsdf_interpolate", "b200tsdf_render", "b200tsdf_mesh",
     "b200tsdf_free", "b200tsdf_save", "b200tsdf_load", "b200tsdf_export_shard", "b200tsdf_import_shard", "b200tsdf_voxel_center", "b200tsdf_voxel_index",
-    "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_frustum_cull",
+    "b200tsdf_get_stats", "b200tsdf_download_nodes", "b200tsdf_download_color_payload", "b200tsdf_frustum_cull",
     "b200tsdf_profile_begin", "b200tsdf_profile_end",
     "b200tsdf_mesh_flatten", "b200tsdf_mesh_cleanup", "b200tsdf_mesh_free", "b200tsdf_meshpost_last_error", "b200tsdf_debug_timing",
 ]
@@ -129,6 +129,7 @@ def load_library() -> C.CDLL:
     lib.b200tsdf_voxel_index.argtypes = [vp, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.b200tsdf_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.b200tsdf_download_nodes.argtypes = [vp, vp, vp, vp, vp, vp, vp]; lib.b200tsdf_download_nodes.restype = C.c_int64
+    lib.b200tsdf_download_color_payload.argtypes = [vp, vp]; lib.b200tsdf_download_color_payload.restype = C.c_int64
     lib.b200tsdf_frustum_cull.argtypes = [vp, vp, vp, vp]
     lib.b200tsdf_profile_begin.argtypes = [vp]
     lib.b200tsdf_profile_end.argtypes = [vp, C.POINTER(Profile)]
@@ -237,15 +238,19 @@ class TSDFVolumeOctree:
     def setIntegrateColor(self, integrate_color: bool):
         self._cfg.integrate_color = int(bool(integrate_color)); self._push()
 
+    def setColorMode(self, color_mode: str):
+        """tsdf_volume_octree.h:290 — "RGB" (default) or "RGBNormalized" (octree.cpp:379-434; fused by the general kernel).
+        "LAB" is refused at reset() (RGB2LAB needs libm pow, octree.cpp:436-470)."""
+        modes = {"RGB": 0, "RGBNormalized": 1, "LAB": 2}
+        if color_mode not in modes:
+            raise ValueError(f"unknown colour mode {color_mode!r}")
+        self._cfg.color_mode = modes[color_mode]; self._push()
+
     def setSensorDistanceBounds(self, min_sensor_dist, max_sensor_dist):
         self._cfg.min_sensor_dist, self._cfg.max_sensor_dist = min_sensor_dist, max_sensor_dist; self._push()
 
     def getSensorDistanceBounds(self):
         return self._cfg.min_sensor_dist, self._cfg.max_sensor_dist
-
-    def setColorMode(self, color_mode: str):
-        if color_mode != "RGB":   # RGBNormalized / LAB are out of scope
-            raise B200Error("only the default colour mode \"RGB\" is supported")
 
     def setNumRandomSplts(self, n: int):
         if n != 1:                # hpp:69-88: rand()-driven, non-deterministic; default 1 (SURVEY.md §2)
@@ -479,7 +484,12 @@ class TSDFVolumeOctree:
         rgb = np.empty((n, 3), np.uint8); M = np.empty(n, np.float32); ns = np.empty(n, np.int32)
         n2 = self._lib.b200tsdf_download_nodes(self._h, _ptr(keys), _ptr(dw), _ptr(flags), _ptr(rgb), _ptr(M), _ptr(ns))
         assert n2 == n
-        return {"keys": keys, "dw": dw, "split": flags, "rgb": rgb, "M": M, "ns": ns}
+        out = {"keys": keys, "dw": dw, "split": flags, "rgb": rgb, "M": M, "ns": ns}
+        if self._cfg.integrate_color and self._cfg.color_mode == 1:
+            q = np.empty((n, 4), np.float32)
+            assert self._lib.b200tsdf_download_color_payload(self._h, _ptr(q)) == n
+            out["rgbn"] = q                                        # {r_n_, g_n_, b_n_, i_} per node
+        return out
 
 
 class MarchingCubesTSDFOctree:

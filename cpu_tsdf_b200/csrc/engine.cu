@@ -249,6 +249,14 @@ __global__ void k_gather_bricks (Params p, const int* __restrict__ list, int n,
     split[(size_t) b * BRICK_SPLIT_WORDS + i] = p.split[s * BRICK_SPLIT_WORDS + i];
 }
 
+__global__ void k_gather_rgbn (Params p, const int* __restrict__ list, int n, float4* __restrict__ out)
+{
+  int b = blockIdx.x;
+  if (b >= n) return;
+  size_t s = (size_t) list[b];
+  for (int i = threadIdx.x; i < BRICK_NODES; i += blockDim.x) out[(size_t) b * BRICK_NODES + i] = p.rgbn[s * BRICK_NODES + i];
+}
+
 // .vol import: claim each brick's slot and copy its payload in
 __global__ void k_load_bricks (Params p, const uint64_t* __restrict__ keys, int n, const float2* __restrict__ nodes, const uint32_t* __restrict__ split,
                                const uchar4* __restrict__ rgb, const float* __restrict__ M, const int* __restrict__ ns)
@@ -394,7 +402,7 @@ struct b200tsdf
   int device = 0, sm_count = 148;
   cudaStream_t stream = nullptr, copy_stream = nullptr, gather_stream = nullptr;   // compute | H2D uploads | pack + NVLink all-gather
   size_t pool = 0;
-  bool alloc_color = false, alloc_var = false;
+  bool alloc_color = false, alloc_var = false, alloc_norm = false;
   size_t root_n = 0;
   int* d_err = nullptr;
   unsigned char* d_frame[2] = { nullptr, nullptr };
@@ -480,6 +488,7 @@ void free_volume (b200tsdf* h)
   cudaFree (h->p.work); h->p.work = nullptr;
   cudaFree (h->p.keys); cudaFree (h->p.nodes); cudaFree (h->p.split); cudaFree (h->p.rgb); cudaFree (h->p.M); cudaFree (h->p.ns);
   cudaFree (h->p.root_dw); cudaFree (h->p.root_split); cudaFree (h->p.root_rgb); cudaFree (h->p.root_M); cudaFree (h->p.root_ns);
+  cudaFree (h->p.rgbn); cudaFree (h->p.root_rgbn); h->p.rgbn = nullptr; h->p.root_rgbn = nullptr;
   h->p.keys = nullptr; h->p.nodes = nullptr; h->p.split = nullptr; h->p.rgb = nullptr; h->p.M = nullptr; h->p.ns = nullptr;
   h->p.root_dw = nullptr; h->p.root_split = nullptr; h->p.root_rgb = nullptr; h->p.root_M = nullptr; h->p.root_ns = nullptr;
   h->pool = 0; h->root_n = 0;
@@ -642,6 +651,9 @@ int b200tsdf_set_config (b200tsdf_t* h, const b200tsdf_config* cfg)
   int dev = h->cfg_pending.device;
   h->cfg_pending = *cfg;
   h->cfg_pending.device = dev;               // a handle is bound to its device at creation
+  // setGlobalTransform is the one setter that does not wait for reset () in the reference: global_transform_ is only read by
+  // save () and the mesher (tsdf_volume_octree.h:131-133, cpp:242, marching_cubes_tsdf_octree.cpp:122-128)
+  std::memcpy (h->cfg.global_transform, cfg->global_transform, sizeof (h->cfg.global_transform));
   return B200TSDF_OK;
 }
 
@@ -661,7 +673,7 @@ int b200tsdf_reset (b200tsdf_t* h)
   Params np = h->p;
   size_t pool = 0, root_n = 0;
   if (const char* msg = derive_params (c, np, pool, root_n)) return h->fail (B200TSDF_EINVAL, msg);
-  bool color = np.color != 0, var = np.track_var != 0;
+  bool color = np.color != 0, var = np.track_var != 0, norm = np.color_norm != 0;
   int C = np.C, Rtop = np.Rtop;
 
   CK (cudaStreamSynchronize (h->stream));
@@ -669,7 +681,7 @@ int b200tsdf_reset (b200tsdf_t* h)
   drop_batch_graphs (h);                                   // captured launches carry the old configuration
   for (int i = 0; i < BATCH_SEGS; ++i) h->bring_used[i] = false;
   h->half_used[0] = h->half_used[1] = false;
-  if (pool != h->pool || root_n != h->root_n || color != h->alloc_color || var != h->alloc_var)
+  if (pool != h->pool || root_n != h->root_n || color != h->alloc_color || var != h->alloc_var || norm != h->alloc_norm)
   {
     h->has_volume = false;                                 // a failed allocation below must not leave a half-built volume usable
     free_volume (h);
@@ -682,8 +694,9 @@ int b200tsdf_reset (b200tsdf_t* h)
     CK (cudaMalloc (&h->p.root_dw, root_n * sizeof (float2)));
     CK (cudaMalloc (&h->p.root_split, ((root_n + 31) / 32) * sizeof (uint32_t)));
     if (color) CK (cudaMalloc (&h->p.root_rgb, root_n * sizeof (uchar4)));
+    if (norm) { CK (cudaMalloc (&h->p.rgbn, pool * BRICK_NODES * sizeof (float4))); CK (cudaMalloc (&h->p.root_rgbn, root_n * sizeof (float4))); }
     if (var) { CK (cudaMalloc (&h->p.root_M, root_n * sizeof (float))); CK (cudaMalloc (&h->p.root_ns, root_n * sizeof (int))); }
-    h->pool = pool; h->root_n = root_n; h->alloc_color = color; h->alloc_var = var;
+    h->pool = pool; h->root_n = root_n; h->alloc_color = color; h->alloc_var = var; h->alloc_norm = norm;
   }
   size_t ncells = (size_t) 1 << (3 * C);
   if (ncells > h->culled_cap)
@@ -695,8 +708,8 @@ int b200tsdf_reset (b200tsdf_t* h)
   {
     // work queues for levels C .. B = L-3 (fast path needs the block-root level at or below the coarse depth)
     int Bl = np.L - 3;
-    h->force_general = c.reserved[0] & 1;
-    h->fast_path = (Bl >= np.C) && !var && !h->force_general && (Bl - np.C + 1 <= MAX_QLEVELS);
+    h->force_general = c.debug_flags & 1;
+    h->fast_path = (Bl >= np.C) && !var && !np.color_norm && !h->force_general && (Bl - np.C + 1 <= MAX_QLEVELS);
     h->q_levels = h->fast_path ? (Bl - np.C + 1) : 0;
     size_t total = 0; size_t caps[MAX_QLEVELS] = {};
     for (int i = 0; i < h->q_levels; ++i)
@@ -718,7 +731,7 @@ int b200tsdf_reset (b200tsdf_t* h)
     h->Q.n = h->d_count;
     // per-cell path
     h->cell_nl = Bl - np.C;
-    h->cell_path = h->fast_path && np.Rtop == np.C && h->cell_nl >= 1 && h->cell_nl <= 3 && !(c.reserved[0] & 2);
+    h->cell_path = h->fast_path && np.Rtop == np.C && h->cell_nl >= 1 && h->cell_nl <= 3 && !(c.debug_flags & 2);
     if (h->cell_path)
     {
       size_t ncell = (size_t) 1 << (3 * np.C);
@@ -734,7 +747,7 @@ int b200tsdf_reset (b200tsdf_t* h)
         h->cellq_cap = need;
       }
     }
-    h->top_path = h->cell_path && h->cell_nl == 3 && !(c.reserved[0] & 4);
+    h->top_path = h->cell_path && h->cell_nl == 3 && !(c.debug_flags & 4);
     size_t bl = h->q_levels ? caps[h->q_levels - 1] : 0;
     if (h->cell_path) bl = std::max (bl, (size_t) h->cell_cap * 512);
     if (bl > h->blist_cap)
@@ -753,6 +766,7 @@ int b200tsdf_reset (b200tsdf_t* h)
     p.work = st.work;
     p.keys = st.keys; p.nodes = st.nodes; p.split = st.split; p.rgb = st.rgb; p.M = st.M; p.ns = st.ns;
     p.root_dw = st.root_dw; p.root_split = st.root_split; p.root_rgb = st.root_rgb; p.root_M = st.root_M; p.root_ns = st.root_ns;
+    p.rgbn = st.rgbn; p.root_rgbn = st.root_rgbn;
   }
   p.err = h->d_err;
   p.diag = h->d_stats + 3;
@@ -770,6 +784,7 @@ int b200tsdf_reset (b200tsdf_t* h)
   k_fill_fresh<<<64, 256, 0, s>>> (p.root_dw, root_n);
   CK (cudaMemsetAsync (p.root_split, 0, ((root_n + 31) / 32) * sizeof (uint32_t), s));
   if (color) CK (cudaMemsetAsync (p.root_rgb, 0, root_n * sizeof (uchar4), s));
+  if (norm) { CK (cudaMemsetAsync (p.rgbn, 0, pool * BRICK_NODES * sizeof (float4), s)); CK (cudaMemsetAsync (p.root_rgbn, 0, root_n * sizeof (float4), s)); }
   if (var) { CK (cudaMemsetAsync (p.root_M, 0, root_n * sizeof (float), s)); CK (cudaMemsetAsync (p.root_ns, 0, root_n * sizeof (int), s)); }
   CK (cudaMemsetAsync (h->d_err, 0, sizeof (int), s));
   *h->h_err = 0;
@@ -1457,6 +1472,7 @@ struct Snapshot
   std::vector<uchar4> rgb; std::vector<float> M; std::vector<int> ns;
   std::vector<float2> root_dw; std::vector<uint32_t> root_split; std::vector<uchar4> root_rgb;
   std::vector<float> root_M; std::vector<int> root_ns;
+  std::vector<float4> rgbn, root_rgbn;
   int err = 0;
 };
 
@@ -1500,6 +1516,16 @@ int take_snapshot (b200tsdf* h, Snapshot& S)
       CK (cudaMemcpy (c_ns.data (), g_ns, c_ns.size () * sizeof (int), cudaMemcpyDeviceToHost));
     }
   }
+  std::vector<float4> c_rgbn;
+  if (dp.rgbn)
+  {
+    float4* g_q = nullptr;
+    CK (cudaMalloc (&g_q, nbz * BRICK_NODES * sizeof (float4)));
+    if (nb) k_gather_rgbn<<<nb, 128, 0, s>>> (dp, d_list, nb, g_q);
+    c_rgbn.resize ((size_t) nb * BRICK_NODES);
+    if (nb) CK (cudaMemcpy (c_rgbn.data (), g_q, c_rgbn.size () * sizeof (float4), cudaMemcpyDeviceToHost));
+    cudaFree (g_q);
+  }
   cudaFree (d_list); cudaFree (g_nodes); cudaFree (g_split); cudaFree (g_rgb); cudaFree (g_M); cudaFree (g_ns);
   // compact directory
   size_t hp = 16;
@@ -1510,6 +1536,8 @@ int take_snapshot (b200tsdf* h, Snapshot& S)
   S.split.assign (hp * BRICK_SPLIT_WORDS, 0u);
   if (dp.rgb) S.rgb.assign (hp * BRICK_NODES, make_uchar4 (0, 0, 0, 0));
   if (dp.M) { S.M.assign (hp * BRICK_NODES, 0.f); S.ns.assign (hp * BRICK_NODES, 0); }
+  if (dp.rgbn) S.rgbn.assign (hp * BRICK_NODES, make_float4 (0.f, 0.f, 0.f, 0.f));
+  S.p.rgbn = dp.rgbn ? S.rgbn.data () : nullptr;
   S.p.keys = S.keys.data (); S.p.pool_mask = (uint32_t) (hp - 1);
   S.p.nodes = S.nodes.data (); S.p.split = S.split.data ();
   S.p.rgb = dp.rgb ? S.rgb.data () : nullptr; S.p.M = dp.M ? S.M.data () : nullptr; S.p.ns = dp.M ? S.ns.data () : nullptr;
@@ -1522,6 +1550,7 @@ int take_snapshot (b200tsdf* h, Snapshot& S)
     std::memcpy (&S.nodes[(size_t) slot * BRICK_NODES], &c_nodes[(size_t) i * BRICK_NODES], BRICK_NODES * sizeof (float2));
     std::memcpy (&S.split[(size_t) slot * BRICK_SPLIT_WORDS], &c_split[(size_t) i * BRICK_SPLIT_WORDS], BRICK_SPLIT_WORDS * sizeof (uint32_t));
     if (dp.rgb) std::memcpy (&S.rgb[(size_t) slot * BRICK_NODES], &c_rgb[(size_t) i * BRICK_NODES], BRICK_NODES * sizeof (uchar4));
+    if (dp.rgbn) std::memcpy (&S.rgbn[(size_t) slot * BRICK_NODES], &c_rgbn[(size_t) i * BRICK_NODES], BRICK_NODES * sizeof (float4));
     if (dp.M)
     {
       std::memcpy (&S.M[(size_t) slot * BRICK_NODES], &c_M[(size_t) i * BRICK_NODES], BRICK_NODES * sizeof (float));
@@ -1533,7 +1562,8 @@ int take_snapshot (b200tsdf* h, Snapshot& S)
   CK (cudaMemcpy (S.root_dw.data (), dp.root_dw, rn * sizeof (float2), cudaMemcpyDeviceToHost));
   CK (cudaMemcpy (S.root_split.data (), dp.root_split, S.root_split.size () * sizeof (uint32_t), cudaMemcpyDeviceToHost));
   S.p.root_dw = S.root_dw.data (); S.p.root_split = S.root_split.data ();
-  S.p.root_rgb = nullptr; S.p.root_M = nullptr; S.p.root_ns = nullptr;
+  S.p.root_rgb = nullptr; S.p.root_M = nullptr; S.p.root_ns = nullptr; S.p.root_rgbn = nullptr;
+  if (dp.root_rgbn) { S.root_rgbn.resize (rn); CK (cudaMemcpy (S.root_rgbn.data (), dp.root_rgbn, rn * sizeof (float4), cudaMemcpyDeviceToHost)); S.p.root_rgbn = S.root_rgbn.data (); }
   if (dp.root_rgb) { S.root_rgb.resize (rn); CK (cudaMemcpy (S.root_rgb.data (), dp.root_rgb, rn * sizeof (uchar4), cudaMemcpyDeviceToHost)); S.p.root_rgb = S.root_rgb.data (); }
   if (dp.root_M)
   {
@@ -1545,21 +1575,26 @@ int take_snapshot (b200tsdf* h, Snapshot& S)
   return B200TSDF_OK;
 }
 
-struct NodeRec { int32_t k[4]; float d, w; uint8_t split, r, g, b; float M; int32_t ns; };
+struct NodeRec { int32_t k[4]; float d, w; uint8_t split, r, g, b; float M; int32_t ns; float q[4]; };
 
 void node_payload (const Params& p, const NodePos& n, NodeRec& r)
 {
   float2 dw = *node_dw (p, n);
-  r.d = dw.x; r.w = dw.y; r.r = r.g = r.b = 0; r.M = 0.f; r.ns = 0;
+  r.d = dw.x; r.w = dw.y; r.r = r.g = r.b = 0; r.M = 0.f; r.ns = 0; r.q[0] = r.q[1] = r.q[2] = r.q[3] = 0.f;
+  if (p.color_norm)
+  {
+    const float4 q = *node_rgbn (p, n); r.q[0] = q.x; r.q[1] = q.y; r.q[2] = q.z; r.q[3] = q.w;
+    const uchar4 c = node_get_rgb (p, n); r.r = c.x; r.g = c.y; r.b = c.z;                 // getRGB, octree.cpp:396-402
+  }
   if (n.slot < 0)
   {
-    if (p.root_rgb) { uchar4 c = p.root_rgb[n.idx]; r.r = c.x; r.g = c.y; r.b = c.z; }
+    if (p.root_rgb && !p.color_norm) { uchar4 c = p.root_rgb[n.idx]; r.r = c.x; r.g = c.y; r.b = c.z; }
     if (p.root_M) { r.M = p.root_M[n.idx]; r.ns = p.root_ns[n.idx]; }
   }
   else
   {
     size_t i = (size_t) n.slot * BRICK_NODES + n.idx;
-    if (p.rgb) { uchar4 c = p.rgb[i]; r.r = c.x; r.g = c.y; r.b = c.z; }
+    if (p.rgb && !p.color_norm) { uchar4 c = p.rgb[i]; r.r = c.x; r.g = c.y; r.b = c.z; }
     if (p.M) { r.M = p.M[i]; r.ns = p.ns[i]; }
   }
 }
@@ -1580,9 +1615,11 @@ void collect_nodes (const Params& p, const NodePos& n, std::vector<NodeRec>& out
 // OctreeNode::serialize (octree.cpp:289-304) / RGBNode::serialize (:360-367), recursive
 void write_vol_node (const Params& p, std::FILE* f, const NodePos& n, bool have_state)
 {
-  NodeRec r; r.d = -1.f; r.w = 0.f; r.r = r.g = r.b = 0; r.M = 0.f; r.ns = 0;
+  NodeRec r; r.d = -1.f; r.w = 0.f; r.r = r.g = r.b = 0; r.M = 0.f; r.ns = 0; r.q[0] = r.q[1] = r.q[2] = r.q[3] = 0.f;
   if (have_state) node_payload (p, n, r);
-  if (p.color) { std::fwrite (&r.r, 1, 1, f); std::fwrite (&r.g, 1, 1, f); std::fwrite (&r.b, 1, 1, f); }
+  // RGBNormalized::serialize writes sizeof (uint8_t) of each of its four FLOATS, i.e. their first bytes (octree.cpp:417-424)
+  if (p.color_norm) for (int k = 0; k < 4; ++k) std::fwrite (&r.q[k], 1, 1, f);
+  else if (p.color) { std::fwrite (&r.r, 1, 1, f); std::fwrite (&r.g, 1, 1, f); std::fwrite (&r.b, 1, 1, f); }
   std::fwrite (&r.d, 4, 1, f); std::fwrite (&r.w, 4, 1, f);
   std::fwrite (&n.cx, 4, 1, f); std::fwrite (&n.cy, 4, 1, f); std::fwrite (&n.cz, 4, 1, f);
   std::fwrite (&n.size, 4, 1, f); std::fwrite (&r.M, 4, 1, f); std::fwrite (&r.ns, 4, 1, f);
@@ -1648,6 +1685,28 @@ int64_t b200tsdf_download_nodes (b200tsdf_t* h, int32_t* keys, float* dw, uint8_
   return (int64_t) recs.size ();
 }
 
+int64_t b200tsdf_download_color_payload (b200tsdf_t* h, float* out4)
+{
+  if (!h || !h->has_volume || !out4) return B200TSDF_EINVAL;
+  if (!h->p.color_norm) return 0;
+  Snapshot S;
+  int rc = take_snapshot (h, S);
+  if (rc) return rc;
+  const Params& p = S.p;
+  std::vector<NodeRec> recs;
+  int n = 1 << p.C;
+  for (int x = 0; x < n; ++x) for (int y = 0; y < n; ++y) for (int z = 0; z < n; ++z)
+  {
+    NodePos nd;
+    if (!locate_node (p, p.C, x, y, z, nd)) return h->fail (B200TSDF_ESTATE, "coarse cell without storage");
+    collect_nodes (p, nd, recs);
+  }
+  std::sort (recs.begin (), recs.end (), [] (const NodeRec& a, const NodeRec& b) {
+    return std::lexicographical_compare (a.k, a.k + 4, b.k, b.k + 4); });
+  for (size_t i = 0; i < recs.size (); ++i) std::memcpy (out4 + 4 * i, recs[i].q, 16);
+  return (int64_t) recs.size ();
+}
+
 // save (tsdf_volume_octree.cpp:222-245; Octree::serialize octree.cpp:645-657; serializeASCII
 // eigen_extensions.h:249-257)
 int b200tsdf_save (b200tsdf_t* h, const char* path)
@@ -1677,7 +1736,7 @@ int b200tsdf_save (b200tsdf_t* h, const char* path)
     for (int k = 0; k < 4; ++k) { if (k) hd += " "; hd += std::string (width - cell[r * 4 + k].size (), ' ') + cell[r * 4 + k]; }
     hd += "\n";
   }
-  hd += std::string (S.p.color ? "RGB" : "NOCOLOR") + "\n#OCTREEBINARY\n";
+  hd += std::string (S.p.color_norm ? "RGBNormalized" : (S.p.color ? "RGB" : "NOCOLOR")) + "\n#OCTREEBINARY\n";
   std::fwrite (hd.data (), 1, hd.size (), f);
   size_t res[3] = { (size_t) c.xres, (size_t) c.yres, (size_t) c.zres };
   std::fwrite (res, sizeof (size_t), 3, f);
@@ -1827,6 +1886,7 @@ int b200tsdf_export_shard (b200tsdf_t* h, void* buf, size_t capacity, size_t* nb
   if (!h || !nbytes) return B200TSDF_EINVAL;
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "export before reset()");
   if (h->p.Rtop != h->p.C) return h->fail (B200TSDF_EINVAL, "shard export needs a grid whose coarse cells are the top-tier roots");
+  if (h->p.color_norm) return h->fail (B200TSDF_EINVAL, "shard export does not carry the RGBNormalized payload");
   Snapshot S;
   int rc = take_snapshot (h, S);
   if (rc) return rc;

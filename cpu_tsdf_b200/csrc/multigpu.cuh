@@ -244,6 +244,7 @@ int b200tsdf_gather_volume (b200tsdf_t* h, b200tsdf_t* full, int root)
   if (root < 0 || root >= nr) return B200TSDF_EINVAL;
   if (h->p.Rtop != h->p.C) return h->fail (B200TSDF_EINVAL, "shard gather needs a grid whose coarse cells are the top-tier roots");
   if (h->p.track_var) return h->fail (B200TSDF_EINVAL, "shard gather does not carry the variance accumulators");
+  if (h->p.color_norm) return h->fail (B200TSDF_EINVAL, "shard gather does not carry the RGBNormalized payload");
   if (rk == root)
   {
     if (!full || !full->has_volume) return h->fail (B200TSDF_EINVAL, "the root needs a reset full-size handle to gather into");

@@ -59,6 +59,10 @@ inline const char* derive_params (const b200tsdf_config& c, Params& p, size_t& p
                       && c.max_weight >= 0.f && c.max_weight <= 1e9f && c.min_sensor_dist >= 1e-6f && c.max_sensor_dist <= 1e6f) ? 1 : 0;
   }
   p.color = c.integrate_color != 0; p.track_var = c.track_variance != 0;
+  if (c.color_mode == B200TSDF_COLOR_LAB)
+    return "colour mode LAB is not supported: LABNode::addObservation converts through libm pow (octree.cpp:436-470), which the device cannot reproduce bit for bit";
+  if (c.color_mode != B200TSDF_COLOR_RGB && c.color_mode != B200TSDF_COLOR_RGB_NORMALIZED) return "unknown colour mode";
+  p.color_norm = (p.color && c.color_mode == B200TSDF_COLOR_RGB_NORMALIZED) ? 1 : 0;
   p.shard_rank = c.shard_rank; p.shard_count = c.shard_count;
   p.pool_mask = (uint32_t) (pool - 1);
   return nullptr;

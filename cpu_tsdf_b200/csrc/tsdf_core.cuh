@@ -37,6 +37,8 @@
 #if !defined(__CUDACC__)
 struct float2 { float x, y; };
 struct uchar4 { unsigned char x, y, z, w; };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4 (float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline float2 make_float2 (float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 static inline uchar4 make_uchar4 (unsigned char a, unsigned char b, unsigned char c, unsigned char d)
 { uchar4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
@@ -141,6 +143,7 @@ struct Params
   int exact_div_ok;               // 1 when every divisor of the update lies where __fdiv_rn takes its fast path (see div_with)
   int width, height;
   int color, track_var;
+  int color_norm;                 // colour payload is RGBNormalized (setColorMode ("RGBNormalized"), octree.cpp:379-434) instead of RGB
   // sharding: this device owns coarse cells with cell_hash % shard_count == shard_rank
   int shard_rank, shard_count;
   // storage
@@ -154,6 +157,8 @@ struct Params
   float2* root_dw;            // [8^Rtop]
   uint32_t* root_split;       // bitset over 8^Rtop
   uchar4* root_rgb;
+  float4* rgbn;               // [pool][584] {r_n_, g_n_, b_n_, i_} when color_norm, else null
+  float4* root_rgbn;
   float* root_M;
   int* root_ns;
   unsigned char* work;        // [pool] finest-tier bricks: interior level-2 nodes seen by the last update (scheduling hint only)
@@ -415,14 +420,49 @@ B2_HD void reset_node (const Params& p, const NodePos& n)
   if (n.slot < 0)
   {
     if (p.root_rgb) p.root_rgb[n.idx] = make_uchar4 (0, 0, 0, 0);
+    if (p.root_rgbn) p.root_rgbn[n.idx] = make_float4 (0.f, 0.f, 0.f, 0.f);
     if (p.root_M) { p.root_M[n.idx] = 0.f; p.root_ns[n.idx] = 0; }
   }
   else
   {
     size_t i = (size_t) n.slot * BRICK_NODES + n.idx;
     if (p.rgb) p.rgb[i] = make_uchar4 (0, 0, 0, 0);
+    if (p.rgbn) p.rgbn[i] = make_float4 (0.f, 0.f, 0.f, 0.f);
     if (p.M) { p.M[i] = 0.f; p.ns[i] = 0; }
   }
+}
+
+// ---- RGBNormalized payload (octree.cpp:379-402) ----------------------------------------------------------------
+B2_HD float4* node_rgbn (const Params& p, const NodePos& n)
+{ return n.slot < 0 ? &p.root_rgbn[n.idx] : &p.rgbn[(size_t) n.slot * BRICK_NODES + n.idx]; }
+// RGBNormalized::addObservation's colour part (:383-392) with w_ = the node's weight BEFORE this observation, w_new = 1.
+// A black pixel gives i = 0 and r / i = NaN, which the running averages then keep: reproduced, not repaired.
+B2_HD void rgbn_observe (float4& q, float w_old, uint32_t bgra)
+{
+  const float r = (float) ((bgra >> 16) & 0xFFu), g = (float) ((bgra >> 8) & 0xFFu), b = (float) (bgra & 0xFFu);
+  const float wsum = fadd (w_old, 1.f);
+  const float i = sqrtf (fadd (fadd (fmul (r, r), fmul (g, g)), fmul (b, b)));      // (exact integer below 2^24 under the root)
+  const float rf = fdiv (r, i), gf = fdiv (g, i), bf = fdiv (b, i);
+  q.x = fdiv (fadd (fmul (w_old, q.x), fmul (1.f, rf)), wsum);
+  q.y = fdiv (fadd (fmul (w_old, q.y), fmul (1.f, gf)), wsum);
+  q.z = fdiv (fadd (fmul (w_old, q.z), fmul (1.f, bf)), wsum);
+  q.w = fdiv (fadd (fmul (w_old, q.w), fmul (1.f, i)), wsum);
+}
+// float -> uint8_t the way x86-64 compiles it (cvttss2si then a byte truncation): RGBNormalized::getRGB, octree.cpp:396-402
+B2_HD unsigned char f2u8_x86 (float v)
+{
+  const int t = (v >= -2147483648.f && v < 2147483648.f) ? (int) v : INT_MIN;
+  return (unsigned char) t;
+}
+// getRGB of a node of a colour volume
+B2_HD uchar4 node_get_rgb (const Params& p, const NodePos& n)
+{
+  if (p.color_norm)
+  {
+    const float4 q = *node_rgbn (p, n);
+    return make_uchar4 (f2u8_x86 (fmul (q.x, q.w)), f2u8_x86 (fmul (q.y, q.w)), f2u8_x86 (fmul (q.z, q.w)), 0);
+  }
+  return n.slot < 0 ? p.root_rgb[n.idx] : p.rgb[(size_t) n.slot * BRICK_NODES + n.idx];
 }
 
 // ---- the projective observation of a node (hpp:143-161) --------------------------------------
@@ -515,7 +555,7 @@ B2_HD int leaf_update_core (const Params& p, float d_new, bool have_bgra, uint32
 
 B2_HD int leaf_update_values (const Params& p, const Frame& f, const Obs& o, float2& dw, uchar4& c, float& M, int& ns, bool& updated)
 {
-  bool have = p.color && f.rgba_off >= 0;
+  bool have = p.color && !p.color_norm && f.rgba_off >= 0;
   uint32_t bgra = 0;
   if (have) { const unsigned char* b = frame_bgr (f, o.u, o.v); bgra = (uint32_t) b[0] | ((uint32_t) b[1] << 8) | ((uint32_t) b[2] << 16) | ((uint32_t) b[3] << 24); }
   return leaf_update_core (p, o.d_new, have, bgra, dw, c, M, ns, updated);
@@ -528,7 +568,7 @@ B2_HD int leaf_update (const Params& p, const Frame& f, const NodePos& n, const 
   float2 dw = *dwp;
   uchar4 c = make_uchar4 (0, 0, 0, 0);
   uchar4* cp = nullptr;
-  if (p.color) { cp = n.slot < 0 ? &p.root_rgb[n.idx] : &p.rgb[(size_t) n.slot * BRICK_NODES + n.idx]; c = *cp; }
+  if (p.color && !p.color_norm) { cp = n.slot < 0 ? &p.root_rgb[n.idx] : &p.rgb[(size_t) n.slot * BRICK_NODES + n.idx]; c = *cp; }
   float M = 0.f; int ns = 0;
   float* Mp = nullptr; int* np = nullptr;
   if (p.track_var)
@@ -537,12 +577,19 @@ B2_HD int leaf_update (const Params& p, const Frame& f, const NodePos& n, const 
     np = n.slot < 0 ? &p.root_ns[n.idx] : &p.ns[(size_t) n.slot * BRICK_NODES + n.idx];
     M = *Mp; ns = *np;
   }
+  const float w_old = dw.y;
   int rc = leaf_update_values (p, f, o, dw, c, M, ns, updated);
   if (updated)
   {
     *dwp = dw;
     if (cp) *cp = c;
     if (Mp) { *Mp = M; *np = ns; }
+    if (p.color_norm && f.rgba_off >= 0)
+    {
+      float4* qp = node_rgbn (p, n); float4 q = *qp;
+      rgbn_observe (q, w_old, *reinterpret_cast<const uint32_t*> (frame_bgr (f, o.u, o.v)));
+      *qp = q;
+    }
   }
   return rc;
 }
@@ -570,7 +617,13 @@ B2_HD int fresh_leaf_store (const Params& p, const Frame& f, const NodePos& n, c
   {
     cnt.n_updates++;
     *node_dw (p, n) = dw;
-    if (p.color) { if (n.slot < 0) p.root_rgb[n.idx] = c; else p.rgb[(size_t) n.slot * BRICK_NODES + n.idx] = c; }
+    if (p.color && !p.color_norm) { if (n.slot < 0) p.root_rgb[n.idx] = c; else p.rgb[(size_t) n.slot * BRICK_NODES + n.idx] = c; }
+    if (p.color_norm && f.rgba_off >= 0)
+    {
+      float4 q = make_float4 (0.f, 0.f, 0.f, 0.f);                  // constructor state, octree.h:217-223
+      rgbn_observe (q, 0.f, *reinterpret_cast<const uint32_t*> (frame_bgr (f, o.u, o.v)));
+      *node_rgbn (p, n) = q;
+    }
     if (p.track_var)
     {
       if (n.slot < 0) { p.root_M[n.idx] = M; p.root_ns[n.idx] = ns; }
@@ -1090,7 +1143,7 @@ B2_HD void render_pixel (const Params& p, const RenderParams& r, int x, int y, f
       {
         if (p.color)
         {
-          uchar4 c = lf.n.slot < 0 ? p.root_rgb[lf.n.idx] : p.rgb[(size_t) lf.n.slot * BRICK_NODES + lf.n.idx];
+          uchar4 c = node_get_rgb (p, lf.n);
           rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
         }
         else rgb[0] = rgb[1] = rgb[2] = 127;               // OctreeNode::getRGB, octree.cpp:173-178
@@ -1177,7 +1230,7 @@ B2_HD int mc_leaf (const Params& p, const McParams& mc, const NodePos& n, float 
   }
   else if (mc.color_mode == 1 && p.color)
   {
-    uchar4 c = n.slot < 0 ? p.root_rgb[n.idx] : p.rgb[(size_t) n.slot * BRICK_NODES + n.idx];
+    uchar4 c = node_get_rgb (p, n);
     cr = c.x; cg = c.y; cb = c.z;
   }
   for (int i = 0; i < 3 * ntri; ++i)

@@ -30,6 +30,10 @@ extern "C" {
 #define B200TSDF_ESTATE     -5   /* call order (e.g. integrate before reset)          */
 #define B200TSDF_EIO        -6   /* file I/O                                          */
 
+#define B200TSDF_COLOR_RGB             0
+#define B200TSDF_COLOR_RGB_NORMALIZED  1
+#define B200TSDF_COLOR_LAB             2   /* not supported: b200tsdf_reset returns B200TSDF_EINVAL */
+
 typedef struct b200tsdf b200tsdf_t;
 
 /* Mirrors the TSDFVolumeOctree setters; defaults = its constructor
@@ -50,7 +54,10 @@ typedef struct b200tsdf_config
   int32_t device;                           /* CUDA device ordinal                                */
   int32_t pool_log2;                        /* brick pool capacity = 2^pool_log2 (0 = default 20) */
   int32_t shard_rank, shard_count;          /* this handle owns coarse cells with hash(cell) % shard_count == shard_rank */
-  int32_t reserved[4];                      /* [0] debug — bit0: general depth-first update kernel only; bit1: per-level upper sweeps instead of the fused per-cell ones; bit2: generic per-cell sweeps instead of the speculative tier-1 ones */
+  int32_t debug_flags;                      /* bit0: general depth-first update kernel only; bit1: per-level upper sweeps instead of the fused per-cell ones; bit2: generic per-cell sweeps instead of the speculative tier-1 ones */
+  int32_t color_mode;                       /* setColorMode (tsdf_volume_octree.h:290) — B200TSDF_COLOR_RGB (default) or B200TSDF_COLOR_RGB_NORMALIZED
+                                               (octree.cpp:379-434; fused by the general kernel).  "LAB" (octree.cpp:436-581) is refused: RGB2LAB needs libm pow */
+  int32_t reserved[2];
   double  global_transform[16];             /* setGlobalTransform tsdf_volume_octree.h:119; row-major 4x4 */
 } b200tsdf_config;
 
@@ -255,6 +262,9 @@ int  b200tsdf_profile_end (b200tsdf_t* h, b200tsdf_profile* out);
  * flags bit0 = has children; rgb 3 bytes; M float; ns int32. */
 int64_t b200tsdf_download_nodes (b200tsdf_t* h, int32_t* keys, float* dw, uint8_t* flags,
                                  uint8_t* rgb, float* M, int32_t* ns);
+/* RGBNormalized volumes: the four floats {r_n_, g_n_, b_n_, i_} of every node, in the order of b200tsdf_download_nodes
+ * (returns the node count, or 0 when the volume does not carry that payload) */
+int64_t b200tsdf_download_color_payload (b200tsdf_t* h, float* out4);
 /* frustum-culled coarse-cell mask of getFrustumCulledVoxels (cpp:619-652): 8^coarse bytes */
 int  b200tsdf_frustum_cull (b200tsdf_t* h, const double* pose_c2w, uint8_t* mask, int32_t* kept);
 

@@ -55,7 +55,9 @@ struct Affine3d
   const double* data () const { return m; }
 };
 struct TriangleSoup { std::vector<float> xyz; std::vector<std::uint8_t> rgb; std::vector<std::int32_t> polygons; };
+struct PointXYZRGBNormal { float x, y, z, pad = 1.f; float normal_x, normal_y, normal_z, npad = 0.f; std::uint8_t b = 0, g = 0, r = 0, a = 255; float curvature = 0.f, cpad[2] = { 0.f, 0.f }; };
 #else
+using pcl::PointXYZRGBNormal;
 using pcl::PointCloud;
 using pcl::PointNormal;
 using pcl::PointXYZ;
@@ -116,24 +118,47 @@ public:
   void setWeightTruncationLimit (float max_weight) { cfg_.max_weight = max_weight; push (); }
   float getWeightTruncationLimit () const { return cfg_.max_weight; }
   void setGlobalTransform (const Affine3d& trans) { detail::pose_rows (trans, cfg_.global_transform); push (); }
+  Affine3d getGlobalTransform () const                                                              // h:135-137 (also what load () read back)
+  {
+    Affine3d t;
+#ifdef B200TSDF_WITH_PCL
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) t.matrix () (r, c) = cfg_.global_transform[r * 4 + c];
+#else
+    std::memcpy (t.m, cfg_.global_transform, sizeof (double) * 16);
+#endif
+    return t;
+  }
   void setSensorDistanceBounds (float min_sensor_dist, float max_sensor_dist) { cfg_.min_sensor_dist = min_sensor_dist; cfg_.max_sensor_dist = max_sensor_dist; push (); }
   void getSensorDistanceBounds (float& min_sensor_dist, float& max_sensor_dist) const { min_sensor_dist = cfg_.min_sensor_dist; max_sensor_dist = cfg_.max_sensor_dist; }
   void setCameraIntrinsics (double fx, double fy, double cx, double cy) { cfg_.fx = fx; cfg_.fy = fy; cfg_.cx = cx; cfg_.cy = cy; push (); }
   void getCameraIntrinsics (double& fx, double& fy, double& cx, double& cy) const { fx = cfg_.fx; fy = cfg_.fy; cx = cfg_.cx; cy = cfg_.cy; }
   void setMaxVoxelSize (float x, float y, float z) { cfg_.max_cell_x = x; cfg_.max_cell_y = y; cfg_.max_cell_z = z; push (); }
   void setIntegrateColor (bool integrate_color) { cfg_.integrate_color = integrate_color; push (); }
+  // h:289-293.  "RGB" and "RGBNormalized" are fused; any other mode (the reference also knows "LAB") makes the next reset () fail
+  // with B200TSDF_EINVAL instead of silently fusing something else
+  void setColorMode (const std::string& color_mode)
+  {
+    cfg_.color_mode = color_mode == "RGB" ? B200TSDF_COLOR_RGB : (color_mode == "RGBNormalized" ? B200TSDF_COLOR_RGB_NORMALIZED : B200TSDF_COLOR_LAB);
+    push ();
+  }
+  // h:180-184 (sic).  Values other than 1 draw the extra samples with libc rand () (hpp:69-88), which cannot be reproduced: they are
+  // refused — status () becomes B200TSDF_EINVAL and stays so until 1 is set again
+  void setNumRandomSplts (int num_random_splits)
+  { num_random_splits_ = num_random_splits; status_ = num_random_splits == 1 ? 0 : B200TSDF_EINVAL; }
+  int getNumRandomSplits () const { return num_random_splits_; }
   // B200 extension: keep OctreeNode::M_ / nsample_ (octree.cpp:160-161) so that save() writes them as the reference does
   // (they are unused by every default code path; tracking them selects the general, slower update kernel)
   void setTrackVariance (bool track) { cfg_.track_variance = track ? 1 : 0; push (); }
 
   // ---- the volumetric path ----
-  void reset () { status_ = h_ ? b200tsdf_reset (h_) : B200TSDF_ENODEVICE; }                      // cpp:201-219
+  void reset ()                                                                                     // cpp:201-219
+  { status_ = !h_ ? B200TSDF_ENODEVICE : (num_random_splits_ != 1 ? B200TSDF_EINVAL : b200tsdf_reset (h_)); }
 
   // impl/tsdf_volume_octree.hpp:48-103 (normals are unused there as well)
   template <typename PointT, typename NormalT>
   bool integrateCloud (const PointCloud<PointT>& cloud, const PointCloud<NormalT>& /*normals*/, const Affine3d& trans = Affine3d::Identity ())
   {
-    if (!h_) return false;
+    if (!h_ || num_random_splits_ != 1) return false;
     double m[16];
     detail::pose_rows (trans, m);
     status_ = b200tsdf_integrate (h_, cloud.points.data (), sizeof (PointT), detail::xyz_offset<PointT> (),
@@ -185,6 +210,33 @@ public:
     return cloud;
   }
 
+  // cpp:427-450: renderView plus the colour of the voxel under every hit (black where the ray misses)
+  typename PointCloud<PointXYZRGBNormal>::Ptr renderColoredView (const Affine3d& trans = Affine3d::Identity (), int downsampleBy = 1) const
+  {
+    typename PointCloud<PointXYZRGBNormal>::Ptr cloud (new PointCloud<PointXYZRGBNormal>);
+    cloud->width = cfg_.image_width / downsampleBy; cloud->height = cfg_.image_height / downsampleBy;
+    cloud->is_dense = false;
+    cloud->points.resize (static_cast<std::size_t> (cloud->width) * cloud->height);
+    std::vector<std::uint8_t> rgb (cloud->points.size () * 3);
+    double m[16];
+    detail::pose_rows (trans, m);
+    PointXYZRGBNormal probe{};
+    int noff = static_cast<int> (reinterpret_cast<const char*> (&probe.normal_x) - reinterpret_cast<const char*> (&probe));
+    if (b200tsdf_render (h_, m, downsampleBy, cloud->points.data (), sizeof (PointXYZRGBNormal), detail::xyz_offset<PointXYZRGBNormal> (), noff, rgb.data ()) != 0) return cloud;
+    for (std::size_t i = 0; i < cloud->points.size (); ++i) { auto& p = cloud->points[i]; p.r = rgb[3 * i]; p.g = rgb[3 * i + 1]; p.b = rgb[3 * i + 2]; }
+    return cloud;
+  }
+
+  // getTSDFValue / interpolateTrilinearly (cpp:454-541; protected in the reference, public here for the callers that subclassed it)
+  float getTSDFValue (float x, float y, float z, bool* valid = nullptr) const
+  {
+    float p[3] = { x, y, z }, v = 0.f; std::uint8_t ok = valid ? (*valid ? 1 : 0) : 1;
+    if (b200tsdf_interpolate (h_, p, 1, &v, &ok) != 0) ok = 0;
+    if (valid) *valid = ok != 0;
+    return v;
+  }
+  float interpolateTrilinearly (float x, float y, float z, bool* valid = nullptr) const { return getTSDFValue (x, y, z, valid); }
+
   void save (const std::string& filename) const { if (h_) b200tsdf_save (h_, filename.c_str ()); }   // cpp:222-245
   void load (const std::string& filename)                                                           // cpp:248-275
   { if (h_) { status_ = b200tsdf_load (h_, filename.c_str ()); b200tsdf_get_config (h_, &cfg_); } }
@@ -194,12 +246,25 @@ public:
   bool getVoxelIndex (float x, float y, float z, int& x_i, int& y_i, int& z_i) const               // cpp:562-574
   { std::int32_t o[3] = { 0, 0, 0 }, in = 0; b200tsdf_voxel_index (h_, x, y, z, o, &in); x_i = o[0]; y_i = o[1]; z_i = o[2]; return in != 0; }
 
+  // TSDFInterface::instantiateFromFile (src/lib/tsdf_interface.cpp:44-51): "for now everything is an octree"
+  static Ptr instantiateFromFile (const std::string& filename, int device = 0, int pool_log2 = 0)
+  {
+    Ptr tsdf (new TSDFVolumeOctree (device, pool_log2));
+    tsdf->load (filename);
+    return tsdf;
+  }
+
 private:
   void push () { if (h_) status_ = b200tsdf_set_config (h_, &cfg_); }
+  int num_random_splits_ = 1;
   b200tsdf_config cfg_{};
   b200tsdf_t* h_ = nullptr;
   mutable int status_ = 0;
 };
+
+// cpu_tsdf::TSDFInterface (include/cpu_tsdf/tsdf_interface.h:64-148): the reference's abstract surface has one implementation, and so
+// does this one
+typedef TSDFVolumeOctree TSDFInterface;
 
 class MarchingCubesTSDFOctree
 {

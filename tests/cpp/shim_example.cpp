@@ -40,5 +40,27 @@ int main ()
   if (!mc.reconstruct (mesh) || mesh.xyz.empty ()) return 1;
   std::printf ("mesh: %zu triangles\n", mesh.xyz.size () / 9);
   tsdf->save ("/tmp/shim_example.vol");
+  // the rest of the surface a reference user compiles against: coloured render, global transform round trip through a .vol,
+  // instantiateFromFile, direct TSDF values, the colour-mode / random-split setters
+  Affine3d gt; gt.m[3] = 0.25; gt.m[7] = -0.5;
+  tsdf->setGlobalTransform (gt);
+  tsdf->save ("/tmp/shim_example_gt.vol");
+  TSDFInterface::Ptr back = TSDFInterface::instantiateFromFile ("/tmp/shim_example_gt.vol", 0, 14);
+  if (!back->ok () || back->getGlobalTransform ().m[3] != 0.25 || back->getGlobalTransform ().m[7] != -0.5) { std::printf ("instantiateFromFile / getGlobalTransform: %s\n", back->lastError ()); return 1; }
+  PointCloud<PointXYZRGBNormal>::Ptr col = back->renderColoredView (pose, 4);
+  const PointXYZRGBNormal& cc = col->points[(col->height / 2) * col->width + col->width / 2];
+  std::printf ("renderColoredView centre depth %f rgb %d %d %d (a colourless volume renders 127)\n", cc.z, cc.r, cc.g, cc.b);
+  if (std::fabs (cc.z - 1.0f) > 0.01f || cc.r != 127 || cc.g != 127 || cc.b != 127) return 1;
+  bool valid = true;
+  float tv = back->getTSDFValue (0.01f, 0.02f, -0.012f, &valid);
+  std::printf ("getTSDFValue %f valid %d\n", tv, valid);
+  if (!valid || std::fabs (tv - 0.4f) > 0.15f) return 1;
+  tsdf->setNumRandomSplts (4);                        // refused loudly, not ignored
+  if (tsdf->integrateCloud (cloud, PointCloud<PointXYZ> (), pose) || tsdf->status () != B200TSDF_EINVAL) return 1;
+  tsdf->setNumRandomSplts (1);
+  tsdf->setColorMode ("LAB"); tsdf->reset ();
+  if (tsdf->status () != B200TSDF_EINVAL) { std::printf ("LAB was not refused\n"); return 1; }
+  tsdf->setColorMode ("RGBNormalized"); tsdf->setIntegrateColor (true); tsdf->reset ();
+  if (tsdf->status () != 0) { std::printf ("RGBNormalized: %s\n", tsdf->lastError ()); return 1; }
   return 0;
 }

@@ -278,7 +278,7 @@ def _engine_2048(general=False, pool_log2=18):
     v.setResolution(2048, 2048, 2048); v.setGridSize(10.0, 10.0, 10.0)
     v.setCameraIntrinsics(525.0, 525.0, CAM.cx, CAM.cy); v.setIntegrateColor(True)
     if general:
-        v._cfg.reserved[0] = 1            # debug switch: general depth-first update kernel only
+        v._cfg.debug_flags = 1            # debug switch: general depth-first update kernel only
         v._push()
     v.reset()
     return v
@@ -398,3 +398,35 @@ def test_get_tsdf_value_direct_entry_point():
         fin = ~np.isnan(va)
         assert np.array_equal(va[fin].view(np.uint32), vb[fin].view(np.uint32))
     assert e.getTSDFValue(pts, True)[1].sum() > 500
+
+
+def test_rgb_normalized_payload_in_the_engine(tmp_path):
+    """setColorMode ("RGBNormalized") (tsdf_volume_octree.h:290; RGBNormalized::addObservation / getRGB / serialize, octree.cpp:379-434):
+    the four floats of every node, the uint8 colours getRGB derives from them (renderColoredView, mesh colours) and the .vol bytes —
+    against the restatement, which tests/test_ref_pin.py pins to the reference for exactly this payload."""
+    o = OracleVolume(**CFG_256, integrate_color=1, color_mode=1); o.reset()
+    e = pkg.TSDFVolumeOctree(device=0, pool_log2=17, track_variance=True)      # (M_ / nsample_ are part of the .vol bytes)
+    e.setResolution(256, 256, 256); e.setGridSize(3.0, 3.0, 3.0); e.setCameraIntrinsics(525.0, 525.0, CAM.cx, CAM.cy)
+    e.setIntegrateColor(True); e.setColorMode("RGBNormalized"); e.reset()
+    for pose, cloud in frames(synth.S1, 5, stride=7, color=True, noise_seed=5):
+        o.integrate(cloud, pose); e.integrateCloud(cloud, None, pose)
+    da, db = o.dump_nodes(), e.download_nodes()
+    assert_same_nodes(da, db, rgb=True)
+    assert np.array_equal(da["rgbn"].view(np.uint32), db["rgbn"].view(np.uint32))          # NaNs of black pixels included, bit for bit
+    assert (da["dw"][:, 1] > 0).sum() > 50000
+    pose = synth.orbit_pose(synth.S1, 10, 100)
+    ra, ca = o.render(pose, 4, colored=True); rb, cb = e.renderColoredView(pose, 4)
+    assert np.array_equal(ra[..., :3], rb[..., :3], equal_nan=True) and np.array_equal(ca, cb) and ca.any()
+    mc = pkg.MarchingCubesTSDFOctree(); mc.setInputTSDF(e); mc.setMinWeight(0.0); mc.setColorByRGB(True)
+    vb, colb, _ = mc.reconstruct()
+    va, cola = o.mesh(0.0, 1)
+    assert len(va) > 3000 and np.array_equal(np.asarray(va).view(np.uint32), np.asarray(vb).reshape(-1, 3).view(np.uint32)) and np.array_equal(cola, colb)
+    pa, pb = str(tmp_path / "a.vol"), str(tmp_path / "b.vol")
+    assert o.save(pa) == 0
+    e.save(pb)
+    assert open(pa, "rb").read() == open(pb, "rb").read()
+    # LAB is refused loudly rather than silently fused as something else
+    lab = pkg.TSDFVolumeOctree(device=0, pool_log2=12)
+    lab.setIntegrateColor(True); lab.setColorMode("LAB")
+    with pytest.raises(pkg.B200Error):
+        lab.reset()
