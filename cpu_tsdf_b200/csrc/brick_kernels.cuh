@@ -228,45 +228,7 @@ __global__ void k_upper_up (Params p, Frame f, Queues Q, int li, unsigned long l
   warp_add_stats (stats, upd, vis);
 }
 
-// ---- 1b/3b. fused upper sweeps: one CTA per culled coarse cell ---------------------------------------------
-// When the block-root level is at most three levels below the coarse depth (2048^3/10 m, 512^3/3 m: C..C+3),
-// the whole upper pyramid of one coarse cell (1 + 8 + 64 nodes + up to 512 block roots) fits in shared memory.
-// k_cell_down walks it level by level inside one CTA (a __syncthreads between levels instead of a kernel
-// launch) and k_cell_up folds it back.  Same per-node rules as k_upper_down / k_upper_up.
-constexpr int CELL_THREADS = 256;
-struct CellRecord { int n[4]; };                 // entries per relative level 0..3 for this cell
-
-__device__ __forceinline__ int upper_visit (const Params& p, const Frame& f, int level, QNode& e, NodePos& n, int& cs,
-                                            unsigned long long& upd)
-{
-  // returns 0 = finished, 1 = interior (children to be visited); e.kind / e.rc are set
-  n = qnode_pos (p, level, e);
-  cs = -1;
-  uint32_t m; uint32_t* sw = split_word (p, n, m);
-  if (*sw & m)                                                      // hpp:122
-  {
-    cs = children_slot (p, n, false);
-    if (cs < 0) { raise_err (p, ERR_MISSING_BRICK); e.kind = KIND_DONE; e.rc = 0; return 0; }
-    e.kind = KIND_OLD;
-    return 1;
-  }
-  Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);
-  if (!o.valid) { e.kind = KIND_DONE; e.rc = 0; return 0; }
-  if (o.near_ && n.size > p.finest_size)                             // hpp:161-166
-  {
-    cs = children_slot (p, n, true);
-    if (cs < 0) { e.kind = KIND_DONE; e.rc = 0; return 0; }
-    e.kind = KIND_NEW;
-    atomicOr (sw, m);                                                // split (): children are fresh by invariant
-    return 1;
-  }
-  bool updated;
-  e.rc = leaf_update (p, f, n, o, updated);
-  e.kind = KIND_DONE;
-  upd += updated;
-  return 0;
-}
-
+// ---- helpers of the bottom-up sweeps ---------------------------------------------------------------------------
 // fold the children's return codes into an interior node (hpp:131-142 / :176-188 + fall-through)
 __device__ __noinline__ int upper_fold_slow (const Params& p, const Frame& f, const NodePos& n, unsigned long long& upd, unsigned long long& vis)
 {
@@ -425,214 +387,7 @@ __device__ __forceinline__ void leaf_visit_slow_lanes (const Params& p, const Fr
   }
 }
 
-constexpr int RC_DEFERRED = 2;   // upper_fold: the node needs the general leaf visit (caller decides how)
-__device__ __forceinline__ int upper_fold (const Params& p, const Frame& f, int level, const QNode& e, bool all_empty,
-                                           unsigned long long& upd, unsigned long long& vis, bool defer_slow = false)
-{
-  if (!all_empty) return 1;                                          // hpp:140 / :185
-  NodePos n = qnode_pos (p, level, e);
-  uint32_t m; uint32_t* sw = split_word (p, n, m);
-  atomicAnd (sw, ~m);                                                // children.clear ()
-  int cs = children_slot (p, n, false);
-  if (cs >= 0) for (int c = 0; c < 8; ++c) reset_node (p, make_child (p, n, c, cs));
-  if (e.kind == KIND_NEW)
-  {
-    Obs o = observe (p, f, n.cx, n.cy, n.cz, n.size);                // same observation as in the down sweep
-    bool updated;
-    int rc = leaf_update (p, f, n, o, updated);                      // hpp:189-214 (falls through after :181)
-    upd += updated;
-    return rc;
-  }
-  if (defer_slow) return RC_DEFERRED;
-  return upper_fold_slow (p, f, n, upd, vis);                        // pre-existing children pruned: leaf visit, may re-split
-}
-
-template <int NL>   // NL = number of levels below the coarse cell down to the block roots (1..3)
-__global__ void __launch_bounds__ (CELL_THREADS) k_cell_down (Params p, Frame f, const QNode* __restrict__ cells, const int* __restrict__ ncells,
-                                                             QNode* __restrict__ gq, CellRecord* __restrict__ recs, int cell_cap,
-                                                             int* __restrict__ blist, int* __restrict__ bcount, unsigned long long* __restrict__ stats)
-{
-  constexpr int CAP1 = 8, CAP2 = NL >= 2 ? 64 : 1, CAP3 = NL >= 3 ? 512 : 1;
-  constexpr int STRIDE = 1 + 8 + (NL >= 2 ? 64 : 0) + (NL >= 3 ? 512 : 0);
-  __shared__ QNode q0, q1[CAP1], q2[CAP2], q3[CAP3];
-  __shared__ int cnt[4];
-  unsigned long long upd = 0, vis = 0;
-  const int tid = threadIdx.x;
-  int count = *ncells;
-  if (count > cell_cap) { if (tid == 0 && blockIdx.x == 0) raise_err (p, ERR_QUEUE_FULL); count = cell_cap; }
-  for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
-  {
-    __syncthreads ();
-    if (tid < 4) cnt[tid] = 0;
-    __syncthreads ();
-    QNode* lvq[4] = { &q0, q1, q2, q3 };
-    if (tid == 0) { q0 = cells[ci]; cnt[0] = 1; }
-    __syncthreads ();
-#pragma unroll
-    for (int rl = 0; rl <= NL; ++rl)
-    {
-      const int level = p.C + rl;
-      const int n_here = cnt[rl];
-      const bool block_level = (rl == NL);
-      for (int base = 0; base < n_here; base += CELL_THREADS)          // warp-uniform trip count
-      {
-        const int i = base + tid;
-        const bool active = i < n_here;
-        QNode e; NodePos n; int cs = -1; int interior = 0;
-        if (active) { e = lvq[rl][i]; vis++; interior = upper_visit (p, f, level, e, n, cs, upd); }
-        if (!block_level)
-        {
-          if (active && interior)
-          {
-            int b = atomicAdd (&cnt[rl + 1], 8);
-            e.child_base = b;
-            for (int c = 0; c < 8; ++c)
-            {
-              NodePos ch = make_child (p, n, c, cs);
-              QNode q; q.x = ch.x; q.y = ch.y; q.z = ch.z; q.slot = ch.slot; q.idx = ch.idx; q.kind = KIND_DONE; q.child_base = -1; q.rc = 0;
-              lvq[rl + 1][b + c] = q;
-            }
-          }
-        }
-        else
-        {
-          // interior block roots -> global block list; the entry index is the node's slot in this cell's record
-          const unsigned lane = tid & 31;
-          const unsigned mask = __ballot_sync (0xffffffffu, active && interior);
-          if (mask)
-          {
-            int b = 0;
-            const int leader = __ffs (mask) - 1;
-            if ((int) lane == leader) b = atomicAdd (bcount, __popc (mask));
-            b = __shfl_sync (0xffffffffu, b, leader);
-            if (active && interior)
-            {
-              e.child_base = cs;
-              blist[b + __popc (mask & ((1u << lane) - 1))] = ci * STRIDE + (NL == 1 ? 1 : (NL == 2 ? 9 : 73)) + i;
-            }
-          }
-        }
-        if (active) lvq[rl][i] = e;
-      }
-      __syncthreads ();
-    }
-    // spill this cell's queues for the block kernel and the bottom-up sweep
-    QNode* g = gq + (size_t) ci * STRIDE;
-    if (tid == 0) { g[0] = q0; recs[ci].n[0] = 1; recs[ci].n[1] = cnt[1]; recs[ci].n[2] = NL >= 2 ? cnt[2] : 0; recs[ci].n[3] = NL >= 3 ? cnt[3] : 0; }
-    for (int i = tid; i < cnt[1]; i += CELL_THREADS) g[1 + i] = q1[i];
-    if (NL >= 2) for (int i = tid; i < cnt[2]; i += CELL_THREADS) g[9 + i] = q2[i];
-    if (NL >= 3) for (int i = tid; i < cnt[3]; i += CELL_THREADS) g[73 + i] = q3[i];
-  }
-  __syncwarp ();
-  warp_add_stats (stats, upd, vis);
-}
-
-template <int NL>
-__global__ void __launch_bounds__ (CELL_THREADS) k_cell_up (Params p, Frame f, const int* __restrict__ ncells, QNode* __restrict__ gq,
-                                                           const CellRecord* __restrict__ recs, int cell_cap, unsigned long long* __restrict__ stats)
-{
-  constexpr int STRIDE = 1 + 8 + (NL >= 2 ? 64 : 0) + (NL >= 3 ? 512 : 0);
-  const int off[4] = { 0, 1, 9, 73 };
-  __shared__ int slow[64];
-  __shared__ int nslow;
-  unsigned long long upd = 0, vis = 0;
-  const int tid = threadIdx.x;
-  int count = *ncells;
-  if (count > cell_cap) count = cell_cap;
-  for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
-  {
-    QNode* g = gq + (size_t) ci * STRIDE;
-    const CellRecord r = recs[ci];
-    // block roots that k_blocks handed back (prune-then-resplit inside the block, nothing committed):
-    // redo them with the general depth-first routine before their parents are folded
-    for (int i = tid; i < r.n[NL]; i += CELL_THREADS)
-    {
-      const QNode e = g[off[NL] + i];
-      if (e.rc != RC_DEFERRED) continue;
-      NodePos n = qnode_pos (p, p.C + NL, e);
-      if (e.kind == KIND_NEW) { uint32_t m; uint32_t* sw = split_word (p, n, m); atomicAnd (sw, ~m); }   // undo the speculative split
-      g[off[NL] + i].rc = upper_fold_slow (p, f, n, upd, vis);
-    }
-    for (int rl = NL - 1; rl >= 0; --rl)
-    {
-      if (tid == 0) nslow = 0;
-      __syncthreads ();                                                // child return codes of level rl+1 are final
-      const int level = p.C + rl;
-      for (int i = tid; i < r.n[rl]; i += CELL_THREADS)
-      {
-        QNode e = g[off[rl] + i];
-        if (e.kind == KIND_DONE) continue;
-        const QNode* ch = g + off[rl + 1] + e.child_base;
-        bool all_empty = true;
-        for (int c = 0; c < 8; ++c) all_empty &= (ch[c].rc < 0);
-        int rc = upper_fold (p, f, level, e, all_empty, upd, vis, true);
-        if (rc == RC_DEFERRED) slow[atomicAdd (&nslow, 1)] = i;         // at most 64 interior nodes per level per cell
-        else g[off[rl] + i].rc = rc;
-      }
-      __syncthreads ();
-      // the rare leaf-visit-after-prune cases: one warp, eight children in parallel
-      if (tid < 32)
-        for (int k = 0; k < nslow; ++k)
-        {
-          const int i = slow[k];
-          const QNode e = g[off[rl] + i];
-          NodePos n = qnode_pos (p, level, e);
-          int rc = leaf_visit_warp8 (p, f, n, upd, vis);
-          if (tid == 0) g[off[rl] + i].rc = rc;
-        }
-      __threadfence_block ();
-      __syncthreads ();
-    }
-  }
-  __syncwarp ();
-  warp_add_stats (stats, upd, vis);
-}
-
-// ---- 2. one warp per interior block root ------------------------------------------------------------------
-// Block roots (level B = L-3) are evaluated by k_upper_down like every other upper node; only the
-// ones that have (or get) children are appended to the block list, with the brick slot cached in
-// QNode::child_base.  Each warp stages one brick (8 + 64 + 512 nodes, 4.7 KB, + 2.3 KB colour) in
-// shared memory, runs updateVoxel's top-down and bottom-up passes over it with ballots, and writes
-// back only what changed.
-constexpr int BLK_WARPS = 4;
-
-// ---- TMA (bulk async copy) staging of a brick: cp.async.bulk global -> shared, completion on an mbarrier ----
-__device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t) __cvta_generic_to_shared (p); }
-__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
-{ asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
-{ asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void tma_bulk_g2s (void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
-{
-  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                :: "r"(smem_u32 (dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
-}
-// bounded wait: a protocol mistake must not be able to hang the device
-__device__ __forceinline__ bool mbar_wait (uint64_t* bar, uint32_t parity)
-{
-  for (int it = 0; it < (1 << 22); ++it)
-  {
-    uint32_t done;
-    asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                  : "=r"(done) : "r"(smem_u32 (bar)), "r"(parity) : "memory");
-    if (done) return true;
-  }
-  return false;
-}
-__device__ __forceinline__ void fence_proxy_async_smem () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-struct WarpSmem
-{
-  float2 dw[BRICK_NODES];       // 4672 B
-  uchar4 rgb[BRICK_NODES];      // 2336 B (colour volumes only)
-  float dnew[72];               // saved observation of level-1/2 nodes split this frame (fall-through update)
-  int uv[72];
-  uint64_t bar;                 // mbarrier of this warp's TMA staging
-  uint64_t pad_;
-  signed char rc3[512];         // return codes of the visited finest voxels
-  uint32_t dirty3[16];          // finest voxels whose state changed (bit j3)
-};
-
+// ---- 2. one warp per interior block root: k_bricks, brick_direct.cuh ------------------------------------------------------
 __device__ __forceinline__ void path_center (const float* c0, float off, int k, int j, float* c)
 {
   // centre of the level-k node with hierarchical index j below a root centred at c0 (octree.cpp:251-264)
@@ -647,316 +402,6 @@ __device__ __forceinline__ void path_center (const float* c0, float off, int k, 
   }
   c[0] = x; c[1] = y; c[2] = z;
 }
-
-// visit one node whose state sits at smem index si.  Returns kind; rc for finished nodes.
-__device__ __forceinline__ int visit_node (const Params& p, const Frame& f, WarpSmem& S, int si, bool split_old,
-                                           const float* c, double near_thr, bool can_split, int& rc, bool& updated)
-{
-  rc = 0; updated = false;
-  if (split_old) return KIND_OLD;
-  Obs o = observe_thr (p, f, c[0], c[1], c[2], near_thr);
-  if (!o.valid) return KIND_DONE;
-  if (can_split && o.near_)
-  {
-    S.dnew[si] = o.d_new; S.uv[si] = o.u | (o.v << 16);
-    return KIND_NEW;
-  }
-  float M = 0.f; int ns = 0;
-  rc = leaf_update_values (p, f, o, S.dw[si], S.rgb[si], M, ns, updated);
-  return KIND_DONE;
-}
-
-// fall-through update of a node whose children were all pruned (hpp:134-137 / :179-182 then :189-214).
-// Returns false when the general path must take over (pre-existing children pruned and the node re-splits).
-__device__ __forceinline__ bool fallthrough_node (const Params& p, const Frame& f, WarpSmem& S, int si, int kind,
-                                                  const float* c, double near_thr, int& rc, bool& updated)
-{
-  Obs o; updated = false;
-  if (kind == KIND_NEW) { o.valid = true; o.near_ = true; o.d_new = S.dnew[si]; o.u = S.uv[si] & 0xFFFF; o.v = S.uv[si] >> 16; }
-  else
-  {
-    o = observe_thr (p, f, c[0], c[1], c[2], near_thr);
-    if (!o.valid) { rc = 0; return true; }
-    if (o.near_) return false;
-  }
-  float M = 0.f; int ns = 0;
-  rc = leaf_update_values (p, f, o, S.dw[si], S.rgb[si], M, ns, updated);
-  return true;
-}
-
-template <bool COLOR>
-#ifndef B2_BLK_MINB
-#define B2_BLK_MINB 6
-#endif
-__global__ void __launch_bounds__ (BLK_WARPS * 32, B2_BLK_MINB) k_blocks (Params p, Frame f, Queues Q, int li,
-                                                                const int* __restrict__ blist, const int* __restrict__ bcount,
-                                                                int* __restrict__ bail, int* __restrict__ bail_count,
-                                                                int* __restrict__ next_work, unsigned long long* __restrict__ stats)
-{
-  __shared__ __align__ (16) WarpSmem smem[BLK_WARPS];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  WarpSmem& S = smem[wib];
-  if (lane == 0) { mbar_init (&S.bar, 1); asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  __syncwarp ();
-  uint32_t tma_phase = 0;
-  const int B = p.C + li;
-  const int count = *bcount;
-  const int nwarps = gridDim.x * BLK_WARPS;
-  unsigned long long upd = 0, vis = 0, nblk = 0;
-  const float sizeB = level_size (p, B);
-  const float off1 = sizeB * 0.25f;
-  const double thr1 = near_threshold (sizeB * 0.5f), thr2 = near_threshold (sizeB * 0.25f);
-
-  // persistent grid (one resident wave); warps pull bricks from a shared counter so the tail stays short
-  (void) nwarps;
-  for (;;)
-  {
-    int wi = 0;
-    if (lane == 0) wi = atomicAdd (next_work, 1);
-    wi = __shfl_sync (0xffffffffu, wi, 0);
-    if (wi >= count) break;
-    const int qi = blist[wi];
-    const QNode e = Q.q[li][qi];
-    nblk += (lane == 0);
-    const int kindR = e.kind, bslot = e.child_base;
-    float c0[3] = { center1d (p, B, e.x), center1d (p, B, e.y), center1d (p, B, e.z) };
-    float2* gdw = p.nodes + (size_t) bslot * BRICK_NODES;
-    uchar4* grgb = COLOR ? p.rgb + (size_t) bslot * BRICK_NODES : nullptr;
-    uint32_t* gsw = p.split + (size_t) bslot * BRICK_SPLIT_WORDS;
-    // ---- stage the brick with the TMA: one bulk copy per array, completion on the warp's mbarrier ----
-    __syncwarp ();
-    if (lane == 0)
-    {
-      fence_proxy_async_smem ();                  // earlier generic accesses to this buffer precede the async writes
-      const uint32_t bytes = (uint32_t) sizeof (S.dw) + (COLOR ? (uint32_t) sizeof (S.rgb) : 0u);
-      mbar_expect_tx (&S.bar, bytes);
-      tma_bulk_g2s (S.dw, gdw, (uint32_t) sizeof (S.dw), &S.bar);
-      if (COLOR) tma_bulk_g2s (S.rgb, grgb, (uint32_t) sizeof (S.rgb), &S.bar);
-    }
-    const uint32_t s1_old = gsw[0] & 0xFFu;
-    const uint32_t s2_old0 = gsw[1], s2_old1 = gsw[2];
-    if (!mbar_wait (&S.bar, tma_phase)) { if (lane == 0) raise_err (p, ERR_QUEUE_FULL); break; }
-    tma_phase ^= 1u;
-    __syncwarp ();
-
-    bool bail_f = false;
-    unsigned int bupd = 0;
-    uint32_t dirty = 0;                             // bits 0-15 finest i, 16-17 level 2, 18 level 1
-    // ---- level 1 (8 nodes, lanes 0..7) ----
-    int kind1 = KIND_DONE, rc1 = 0;
-    if (lane < 8)
-    {
-      float c[3]; bool u_;
-      path_center (c0, off1, 1, lane, c);
-      kind1 = visit_node (p, f, S, lane, (s1_old >> lane) & 1, c, thr1, true, rc1, u_);
-      if (u_) { dirty |= 1u << 18; bupd++; }
-    }
-    const uint32_t int1 = __ballot_sync (0xffffffffu, kind1 != KIND_DONE);
-    const uint32_t new1 = __ballot_sync (0xffffffffu, kind1 == KIND_NEW);
-    // ---- level 2 (64 nodes: j2 = lane + 32 i2) ----
-    int kind2[2], rc2[2];
-    uint32_t int2[2], new2[2];
-#pragma unroll
-    for (int i2 = 0; i2 < 2; ++i2)
-    {
-      const int j2 = lane + 32 * i2;
-      kind2[i2] = KIND_DONE; rc2[i2] = 0;
-      if ((int1 >> (j2 >> 3)) & 1)
-      {
-        float c[3]; bool u_;
-        path_center (c0, off1, 2, j2, c);
-        kind2[i2] = visit_node (p, f, S, 8 + j2, ((i2 ? s2_old1 : s2_old0) >> lane) & 1, c, thr2, true, rc2[i2], u_);
-        if (u_) { dirty |= 1u << (16 + i2); bupd++; }
-      }
-      int2[i2] = __ballot_sync (0xffffffffu, kind2[i2] != KIND_DONE);
-      new2[i2] = __ballot_sync (0xffffffffu, kind2[i2] == KIND_NEW);
-    }
-    // ---- level 3: the finest voxels.  Only children of interior level-2 nodes are visited (typically about half
-    //      of the block), so they are COMPACTED across lanes: visited voxel t = lane + 32 r is child (t & 7) of the
-    //      (t >> 3)-th interior level-2 node.  Return codes go to shared memory for the bottom-up sweep. ----
-    if (lane < 16) S.dirty3[lane] = 0;
-    __syncwarp ();
-    {
-      const uint32_t m0 = int2[0], m1 = int2[1];
-      const int n0 = __popc (m0), nvis = 8 * (n0 + __popc (m1));
-#pragma unroll 1
-      for (int base = 0; base < nvis; base += 32)
-      {
-        const int t = base + lane;
-        if (t < nvis)
-        {
-          const int rank = t >> 3;
-          const int j2 = rank < n0 ? (int) __fns (m0, 0, rank + 1) : 32 + (int) __fns (m1, 0, rank - n0 + 1);
-          const int j3 = 8 * j2 + (t & 7);
-          float c[3]; bool u_; int rc;
-          path_center (c0, off1, 3, j3, c);
-          visit_node (p, f, S, 72 + j3, false, c, 0.0, false, rc, u_);
-          S.rc3[j3] = (signed char) rc;
-          if (u_) { atomicOr (&S.dirty3[j3 >> 5], 1u << (j3 & 31)); bupd++; }
-        }
-      }
-    }
-    __syncwarp ();
-    // ---- bottom-up: level 2 ----
-    uint32_t pruned2[2], nonneg2[2];
-#pragma unroll
-    for (int i2 = 0; i2 < 2; ++i2)
-    {
-      const int j2 = lane + 32 * i2;
-      bool pruned = false;
-      if (kind2[i2] != KIND_DONE)
-      {
-        const uint2 r8 = *reinterpret_cast<const uint2*> (&S.rc3[8 * j2]);               // the eight children's codes (-1 = 0xFF)
-        if (!(r8.x == 0xFFFFFFFFu && r8.y == 0xFFFFFFFFu)) rc2[i2] = 1;
-        else
-        {
-          pruned = true;
-          float c[3]; bool u_;
-          path_center (c0, off1, 2, j2, c);
-          if (!fallthrough_node (p, f, S, 8 + j2, kind2[i2], c, thr2, rc2[i2], u_)) bail_f = true;
-          if (u_) { dirty |= 1u << (16 + i2); bupd++; }
-        }
-      }
-      pruned2[i2] = __ballot_sync (0xffffffffu, pruned);
-      nonneg2[i2] = __ballot_sync (0xffffffffu, ((int1 >> (j2 >> 3)) & 1) && rc2[i2] >= 0);
-    }
-    if (pruned2[0] | pruned2[1])                    // children of pruned level-2 nodes return to the fresh state
-    {
-#pragma unroll 1
-      for (int i = 0; i < 16; ++i)
-      {
-        const int j2 = (lane + 32 * i) >> 3;
-        if (((j2 < 32 ? pruned2[0] : pruned2[1]) >> (j2 & 31)) & 1)
-        {
-          S.dw[72 + lane + 32 * i] = make_float2 (-1.f, 0.f);
-          if (COLOR) S.rgb[72 + lane + 32 * i] = make_uchar4 (0, 0, 0, 0);
-          atomicOr (&S.dirty3[i], 1u << lane);
-        }
-      }
-    }
-    __syncwarp ();
-    // ---- bottom-up: level 1 ----
-    bool pruned1f = false;
-    if (lane < 8 && kind1 != KIND_DONE)
-    {
-      const uint32_t nn = nonneg2[lane >> 2];
-      if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc1 = 1;
-      else
-      {
-        pruned1f = true;
-        float c[3]; bool u_;
-        path_center (c0, off1, 1, lane, c);
-        if (!fallthrough_node (p, f, S, lane, kind1, c, thr1, rc1, u_)) bail_f = true;
-        if (u_) { dirty |= 1u << 18; bupd++; }
-      }
-    }
-    const uint32_t pruned1 = __ballot_sync (0xffffffffu, pruned1f);
-    const uint32_t nonneg1 = __ballot_sync (0xffffffffu, lane < 8 && rc1 >= 0);
-    if (pruned1)
-    {
-#pragma unroll
-      for (int i2 = 0; i2 < 2; ++i2)
-      {
-        const int j2 = lane + 32 * i2;
-        if ((pruned1 >> (j2 >> 3)) & 1)
-        {
-          S.dw[8 + j2] = make_float2 (-1.f, 0.f);
-          if (COLOR) S.rgb[8 + j2] = make_uchar4 (0, 0, 0, 0);
-          dirty |= 1u << (16 + i2);
-        }
-      }
-    }
-    // ---- root (its state lives in the parent tier / root arrays) ----
-    int rcR = 1;
-    const bool prunedR = (nonneg1 & 0xFFu) == 0;
-    bool root_updated = false;
-    NodePos nb;
-    nb.level = B; nb.x = e.x; nb.y = e.y; nb.z = e.z; nb.cx = c0[0]; nb.cy = c0[1]; nb.cz = c0[2]; nb.size = sizeB; nb.slot = e.slot; nb.idx = e.idx;
-    Obs oR; oR.valid = false;
-    if (prunedR)
-    {
-      oR = observe (p, f, c0[0], c0[1], c0[2], sizeB);
-      if (kindR == KIND_OLD && oR.valid && oR.near_) bail_f = true;
-    }
-    if (__any_sync (0xffffffffu, bail_f))
-    {
-      // nothing has been committed: hand this block root to the general depth-first routine (k_bail)
-      if (lane == 0) { if (bail) bail[atomicAdd (bail_count, 1)] = qi; else { Q.q[li][qi].rc = RC_DEFERRED; atomicAdd (bail_count, 1); } }
-      __syncwarp ();
-      continue;
-    }
-    // ---- commit ----
-    upd += bupd;
-    vis += (lane == 0) ? (8 + 8 * (__popc (int1) + __popc (int2[0]) + __popc (int2[1]))) : 0;
-    __syncwarp ();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i)
-      if ((S.dirty3[i] >> lane) & 1)
-      {
-        gdw[72 + lane + 32 * i] = S.dw[72 + lane + 32 * i];
-        if (COLOR) grgb[72 + lane + 32 * i] = S.rgb[72 + lane + 32 * i];
-      }
-#pragma unroll
-    for (int i2 = 0; i2 < 2; ++i2)
-      if ((dirty >> (16 + i2)) & 1)
-      {
-        gdw[8 + lane + 32 * i2] = S.dw[8 + lane + 32 * i2];
-        if (COLOR) grgb[8 + lane + 32 * i2] = S.rgb[8 + lane + 32 * i2];
-      }
-    if ((dirty >> 18) & 1) { gdw[lane] = S.dw[lane]; if (COLOR) grgb[lane] = S.rgb[lane]; }
-    if (prunedR && lane < 8) { gdw[lane] = make_float2 (-1.f, 0.f); if (COLOR) grgb[lane] = make_uchar4 (0, 0, 0, 0); }
-    if (lane == 0)
-    {
-      const uint32_t s1_new = ((s1_old | (new1 & 0xFFu)) & ~(pruned1 & 0xFFu)) & 0xFFu;   // all zero when the root is pruned
-      const uint32_t s2_new0 = (s2_old0 | new2[0]) & ~pruned2[0];
-      const uint32_t s2_new1 = (s2_old1 | new2[1]) & ~pruned2[1];
-      if (s1_new != s1_old) gsw[0] = s1_new;
-      if (s2_new0 != s2_old0) gsw[1] = s2_new0;
-      if (s2_new1 != s2_old1) gsw[2] = s2_new1;
-      if (prunedR)
-      {
-        uint32_t rm; uint32_t* rsw = split_word (p, nb, rm);
-        atomicAnd (rsw, ~rm);                      // (k_upper_down set the bit for a root split this frame)
-        rcR = 0;
-        if (oR.valid) { rcR = leaf_update (p, f, nb, oR, root_updated); upd += root_updated; }
-      }
-      Q.q[li][qi].rc = rcR;
-    }
-    __syncwarp ();
-  }
-  // warp-reduce the counters, one atomic per warp
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-  {
-    upd += __shfl_down_sync (0xffffffffu, upd, o);
-    vis += __shfl_down_sync (0xffffffffu, vis, o);
-  }
-  if (lane == 0)
-  {
-    if (upd) atomicAdd (&stats[0], upd);
-    if (vis) atomicAdd (&stats[1], vis);
-    if (nblk) atomicAdd (&stats[2], nblk);
-  }
-}
-
-// the rare non-separable case: redo the block root depth-first on the (untouched) global state
-__global__ void k_bail (Params p, Frame f, Queues Q, int li, const int* __restrict__ bail, const int* __restrict__ bail_count,
-                        unsigned long long* __restrict__ stats)
-{
-  int count = *bail_count;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-  {
-    int qi = bail[i];
-    QNode e = Q.q[li][qi];
-    NodePos n = qnode_pos (p, p.C + li, e);
-    if (e.kind == KIND_NEW) { uint32_t m; uint32_t* sw = split_word (p, n, m); atomicAnd (sw, ~m); }   // undo the speculative split
-    Counters cnt; cnt.n_updates = 0; cnt.n_visits = 0;
-    Q.q[li][qi].rc = update_voxel_dfs (p, f, n, cnt);
-    atomicAdd (&stats[0], (unsigned long long) cnt.n_updates);
-    atomicAdd (&stats[1], (unsigned long long) (cnt.n_visits - 1));
-  }
-}
-
 
 // ---- 1c/3c. upper sweeps for the common shape: coarse cell == root of a tier-1 brick, block roots 3 levels below ----
 // k_celltop_down: one CTA per culled coarse cell.  All 585 nodes of the cell's upper pyramid (cell + 8 + 64 + 512
@@ -996,27 +441,40 @@ struct TopSmem
 __device__ __forceinline__ void top_kj (int f, int& k, int& j)
 { if (f == 0) { k = 0; j = 0; } else if (f < 9) { k = 1; j = f - 1; } else if (f < 73) { k = 2; j = f - 9; } else { k = 3; j = f - 73; } }
 
+// The "cell" of these two kernels is a SUPERCELL: the root of a tier-1 brick, at level SL = L - 6 (its block roots are the 512
+// level-3 nodes of that brick).  Three grid shapes:
+//   C == SL (2048^3 / 10 m, 512^3 / 3 m): the supercells are the culled coarse cells (qslot 0);
+//   C <  SL (4096^3 / 10 m, 1024^3 / 3 m): the coarse levels C .. SL-1 are swept by k_upper_down / k_upper_up and the supercells
+//           are the interior nodes they queued at level SL (qslot SL - C);
+//   C >  SL (256^3 / 3 m, 128^3 / 3 m, ...): the coarse cells lie INSIDE the brick, at relative level C - SL.  Every tier-1 root
+//           is a supercell (static list, qslot < 0); the levels above C are virtual — they exist by Octree::init
+//           (octree.cpp:584-599), carry no state, are never observed, updated or pruned — and a node of level C is visited
+//           only when it passes the frustum cull and belongs to this shard (cpp:619-652), exactly like a queued coarse cell.
 template <bool COLOR>
-__global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const FrameRec* __restrict__ fr, const QNode* __restrict__ cells, int* __restrict__ d_count,
+__global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const FrameRec* __restrict__ fr, QNode* __restrict__ cells, int* __restrict__ d_count,
                                                                QNode* __restrict__ gq, CellTop* __restrict__ tops, int cell_cap,
-                                                               int* __restrict__ blist, int bl_stride, unsigned long long* __restrict__ stats)
+                                                               int* __restrict__ blist, int bl_stride, unsigned long long* __restrict__ stats,
+                                                               int SL, int qslot, int static_count)
 {
   __shared__ __align__ (16) TopSmem S;
   __shared__ Frame s_f_;
+  __shared__ float s_pl_[6][4];
   const int tid = threadIdx.x, lane = tid & 31;
   pdl_launch_dependents ();
   {
     const int* src_ = reinterpret_cast<const int*> (&fr->f); int* dst_ = reinterpret_cast<int*> (&s_f_);
     for (int w_ = tid; w_ < (int) (sizeof (Frame) / sizeof (int)); w_ += TOP_THREADS) dst_[w_] = src_[w_];
+    if (tid < 24) s_pl_[tid >> 2][tid & 3] = fr->pl[tid >> 2][tid & 3];
   }
   int* const cnt_ = d_count + 16 * fr->cset;
   __syncthreads ();
-  pdl_wait ();                                          // everything below reads what k_front wrote
+  pdl_wait ();                                          // everything below reads what the previous kernel wrote
   const Frame& f = s_f_;
   unsigned long long upd = 0, vis = 0;
-  int count = cnt_[0];
+  int count = qslot >= 0 ? cnt_[qslot] : static_count;
   if (count > cell_cap) { if (tid == 0 && blockIdx.x == 0) raise_err (p, ERR_QUEUE_FULL); count = cell_cap; }
-  const float sizeC = level_size (p, p.C);
+  const int cell_lvl = p.C - SL;                        // relative level of the coarse cells (<= 0: the supercell is at or below the coarse depth)
+  const float sizeC = level_size (p, SL);
   const float off1 = sizeC * 0.25f;
   const double thr[4] = { near_threshold (sizeC), near_threshold (sizeC * 0.5f), near_threshold (sizeC * 0.25f), near_threshold (sizeC * 0.125f) };
   for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
@@ -1025,7 +483,7 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
     if (tid == 0)
     {
       S.cell = cells[ci];
-      S.c0[0] = center1d (p, p.C, S.cell.x); S.c0[1] = center1d (p, p.C, S.cell.y); S.c0[2] = center1d (p, p.C, S.cell.z);
+      S.c0[0] = center1d (p, SL, S.cell.x); S.c0[1] = center1d (p, SL, S.cell.y); S.c0[2] = center1d (p, SL, S.cell.z);
     }
     __syncthreads ();
     const QNode cell = S.cell;
@@ -1042,22 +500,32 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
       S.o_flags[n] = (unsigned char) ((o.valid ? 1 : 0) | (o.near_ ? 2 : 0));
       S.kind[n] = KIND_DONE; S.rc[n] = 0; S.dirty[n] = 0;
     }
-    // ---- the cell itself (root arrays) ----
+    // ---- the supercell itself (its state lives in the root arrays or in the tier above; none when it is virtual) ----
     if (tid == 0)
     {
-      NodePos nc; nc.level = p.C; nc.x = cell.x; nc.y = cell.y; nc.z = cell.z; nc.cx = c0[0]; nc.cy = c0[1]; nc.cz = c0[2]; nc.size = sizeC; nc.slot = -1; nc.idx = cell.idx;
-      uint32_t m; uint32_t* sw = split_word (p, nc, m);
       int kind = KIND_DONE, rc = 0, slot = -1;
-      vis++;
-      if (*sw & m) { kind = KIND_OLD; slot = find_brick (p, p.T - 1, cell.x, cell.y, cell.z); if (slot < 0) { raise_err (p, ERR_MISSING_BRICK); kind = KIND_DONE; } }
+      if (cell_lvl > 0)
+      {
+        kind = KIND_OLD;                                               // above the coarse depth: always split, no state
+        slot = find_brick (p, 1, cell.x, cell.y, cell.z);
+        if (slot < 0) { raise_err (p, ERR_MISSING_BRICK); kind = KIND_DONE; }
+      }
       else
       {
-        Obs o = observe_thr (p, f, c0[0], c0[1], c0[2], thr[0]);
-        if (o.valid)
+        NodePos nc; nc.level = SL; nc.x = cell.x; nc.y = cell.y; nc.z = cell.z; nc.cx = c0[0]; nc.cy = c0[1]; nc.cz = c0[2]; nc.size = sizeC; nc.slot = cell.slot; nc.idx = cell.idx;
+        uint32_t m; uint32_t* sw = split_word (p, nc, m);
+        vis++;
+        if (*sw & m) { kind = KIND_OLD; slot = find_brick (p, 1, cell.x, cell.y, cell.z); if (slot < 0) { raise_err (p, ERR_MISSING_BRICK); kind = KIND_DONE; } }
+        else
         {
-          if (o.near_) { slot = find_or_insert_brick (p, p.T - 1, cell.x, cell.y, cell.z); if (slot >= 0) { kind = KIND_NEW; atomicOr (sw, m); } }
-          else { bool u_; rc = leaf_update (p, f, nc, o, u_); upd += u_; }
+          Obs o = observe_thr (p, f, c0[0], c0[1], c0[2], thr[0]);
+          if (o.valid)
+          {
+            if (o.near_) { slot = find_or_insert_brick (p, 1, cell.x, cell.y, cell.z); if (slot >= 0) { kind = KIND_NEW; atomicOr (sw, m); } }
+            else { bool u_; rc = leaf_update (p, f, nc, o, u_); upd += u_; }
+          }
         }
+        if (kind == KIND_DONE) cells[ci].rc = rc;                      // (read by k_upper_up when coarse levels lie above the supercell)
       }
       S.root_interior = kind; S.t1slot = slot;
       S.kind[0] = (unsigned char) kind; S.rc[0] = (signed char) rc;     // (written after the init loop of this thread: n = 0 is tid 0's)
@@ -1095,6 +563,15 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
       {
         const int n = base + j;
         if (S.kind[pbase + (j >> 3)] == KIND_DONE) continue;          // parent is not interior: node not visited
+        if (k < cell_lvl) { S.kind[n] = KIND_OLD; continue; }          // above the coarse depth: virtual
+        if (k == cell_lvl)
+        {
+          // a coarse cell: visited only when its centre passes the frustum cull and this shard owns it (cpp:619-652)
+          float c[3]; path_center (c0, off1, k, j, c);
+          int lx = 0, ly = 0, lz = 0;
+          for (int q = k - 1; q >= 0; --q) { const int cc = (j >> (3 * q)) & 7; lx = (lx << 1) | (cc >> 2); ly = (ly << 1) | ((cc >> 1) & 1); lz = (lz << 1) | (cc & 1); }
+          if (!frustum_contains (s_pl_, c[0], c[1], c[2]) || !owns_cell (p, (cell.x << k) | lx, (cell.y << k) | ly, (cell.z << k) | lz)) continue;
+        }
         vis++;
         const bool sold = (S.split_old[split_word_base (k) + (j >> 5)] >> (j & 31)) & 1;
         int kind = KIND_DONE, rc = 0;
@@ -1170,9 +647,9 @@ __device__ __forceinline__ int top_fallthrough_new (const Params& p, const Frame
 }
 
 template <bool COLOR>
-__global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec* __restrict__ fr, const QNode* __restrict__ cells, const int* __restrict__ d_count,
+__global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec* __restrict__ fr, QNode* __restrict__ cells, const int* __restrict__ d_count,
                                                       const QNode* __restrict__ gq, const CellTop* __restrict__ tops, int cell_cap,
-                                                      unsigned long long* __restrict__ stats)
+                                                      unsigned long long* __restrict__ stats, int SL, int qslot, int static_count)
 {
   // Params / Frame live in shared memory here: the out-of-line slow path takes them by reference, which
   // would otherwise make every thread copy the kernel parameters to its stack in the prologue
@@ -1194,12 +671,13 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   unsigned long long upd = 0, vis = 0;
-  int count = d_count[16 * fr->cset];
+  int count = qslot >= 0 ? d_count[16 * fr->cset + qslot] : static_count;
   if (count > cell_cap) count = cell_cap;
   if (fr->timing && blockIdx.x == 0 && threadIdx.x == 0 && fr->kt[1] > fr->kt[0])
   { atomicAdd (&stats[5], fr->kt[1] - fr->kt[0]); atomicAdd (&stats[6], 1ull); }          // device-timed brick kernel of this frame
-  const float sizeC = level_size (p, p.C);
+  const float sizeC = level_size (p, SL);
   const float off1 = sizeC * 0.25f;
+  const int cell_lvl = p.C - SL;                        // see k_celltop_down
   constexpr int STRIDE = 585;
   const long long c_entry = clock64 ();
   for (int ci = warp; ci < count; ci += nwarps)
@@ -1210,7 +688,7 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
     const int t1 = top->t1slot;
     if (t1 < 0) continue;                                            // the cell was a leaf: nothing to fold
     const QNode cell = cells[ci];
-    const float c0[3] = { center1d (p, p.C, cell.x), center1d (p, p.C, cell.y), center1d (p, p.C, cell.z) };
+    const float c0[3] = { center1d (p, SL, cell.x), center1d (p, SL, cell.y), center1d (p, SL, cell.z) };
     float2* gdw = p.nodes + (size_t) t1 * BRICK_NODES;
     uchar4* grgb = COLOR ? p.rgb + (size_t) t1 * BRICK_NODES : nullptr;
     uint32_t* gsw = p.split + (size_t) t1 * BRICK_SPLIT_WORDS;
@@ -1227,21 +705,6 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
       for (int i = 0; i < 16; ++i) { k3[i] = top->kind[73 + lane + 32 * i]; r3[i] = top->rc[73 + lane + 32 * i]; }
 #pragma unroll
       for (int i = 0; i < 16; ++i) if (k3[i] != KIND_DONE) r3[i] = gq[(size_t) ci * STRIDE + 73 + lane + 32 * i].rc;
-      // block roots that k_blocks handed back untouched (prune-then-resplit inside the block): general path, rare
-#pragma unroll 1
-      for (int i = 0; i < 16; ++i)
-        if (k3[i] != KIND_DONE && r3[i] == RC_DEFERRED)
-        {
-          const int j3 = lane + 32 * i;
-          NodePos n; float c[3];
-          path_center (c0, off1, 3, j3, c);
-          int lx = 0, ly = 0, lz = 0;
-          for (int q = 2; q >= 0; --q) { int cc = (j3 >> (3 * q)) & 7; lx = (lx << 1) | (cc >> 2); ly = (ly << 1) | ((cc >> 1) & 1); lz = (lz << 1) | (cc & 1); }
-          n.level = p.C + 3; n.x = (cell.x << 3) | lx; n.y = (cell.y << 3) | ly; n.z = (cell.z << 3) | lz;
-          n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.125f; n.slot = t1; n.idx = 72 + j3;
-          if (k3[i] == KIND_NEW) atomicAnd (&gsw[4 + (j3 >> 5)], ~(1u << (j3 & 31)));      // undo the speculative split
-          r3[i] = upper_fold_slow (p, f, n, upd, vis);
-        }
 #pragma unroll
       for (int i = 0; i < 16; ++i)
       {
@@ -1264,14 +727,14 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
       NodePos n;
       if (kind2[i2] != KIND_DONE)
       {
-        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc = 1;
+        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0 || 2 < cell_lvl) rc = 1;      // (a virtual level is never pruned)
         else
         {
           // prune: children.clear () -> split bit off, eight block-root nodes back to the fresh state
           atomicAnd (&gsw[1 + (j2 >> 5)], ~(1u << (j2 & 31)));
           for (int c = 0; c < 8; ++c) { gdw[72 + 8 * j2 + c] = make_float2 (-1.f, 0.f); if (COLOR) grgb[72 + 8 * j2 + c] = make_uchar4 (0, 0, 0, 0); }
           float c[3]; path_center (c0, off1, 2, j2, c);
-          n.level = p.C + 2; n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.25f; n.slot = t1; n.idx = 8 + j2;
+          n.level = SL + 2; n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.25f; n.slot = t1; n.idx = 8 + j2;
           { int lx = 0, ly = 0, lz = 0; for (int q = 1; q >= 0; --q) { int cc = (j2 >> (3 * q)) & 7; lx = (lx << 1) | (cc >> 2); ly = (ly << 1) | ((cc >> 1) & 1); lz = (lz << 1) | (cc & 1); }
             n.x = (cell.x << 2) | lx; n.y = (cell.y << 2) | ly; n.z = (cell.z << 2) | lz; }
           if (kind2[i2] == KIND_NEW) { rc = top_fallthrough_new (p, f, n, top->dnew[9 + j2], top->uv[9 + j2], upd); dbg_ft++; }
@@ -1293,13 +756,13 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
       if (lane < 8 && kind1 != KIND_DONE)
       {
         const uint32_t nn = nonneg2[lane >> 2];
-        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0) rc1 = 1;
+        if (((nn >> (8 * (lane & 3))) & 0xFFu) != 0 || 1 < cell_lvl) rc1 = 1;
         else
         {
           atomicAnd (&gsw[0], ~(1u << lane));
           for (int c = 0; c < 8; ++c) { gdw[8 + 8 * lane + c] = make_float2 (-1.f, 0.f); if (COLOR) grgb[8 + 8 * lane + c] = make_uchar4 (0, 0, 0, 0); }
           float c[3]; path_center (c0, off1, 1, lane, c);
-          n.level = p.C + 1; n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.5f; n.slot = t1; n.idx = lane;
+          n.level = SL + 1; n.cx = c[0]; n.cy = c[1]; n.cz = c[2]; n.size = sizeC * 0.5f; n.slot = t1; n.idx = lane;
           n.x = (cell.x << 1) | ((lane >> 2) & 1); n.y = (cell.y << 1) | ((lane >> 1) & 1); n.z = (cell.z << 1) | (lane & 1);
           if (kind1 == KIND_NEW) rc1 = top_fallthrough_new (p, f, n, top->dnew[1 + lane], top->uv[1 + lane], upd);
           else slow = true;
@@ -1312,16 +775,18 @@ __global__ void __launch_bounds__ (128) k_celltop_up (Params gp, const FrameRec*
     const long long cC = clock64 ();
     int dbg_cell = 0;
     // ---- the cell ----
-    if ((nonneg1 & 0xFFu) == 0)
+    int rc_cell = 1;
+    if ((nonneg1 & 0xFFu) == 0 && cell_lvl <= 0)
     {
       dbg_cell = top->kind[0] == KIND_NEW ? 1 : 2;
-      NodePos nc; nc.level = p.C; nc.x = cell.x; nc.y = cell.y; nc.z = cell.z; nc.cx = c0[0]; nc.cy = c0[1]; nc.cz = c0[2]; nc.size = sizeC; nc.slot = -1; nc.idx = cell.idx;
+      NodePos nc; nc.level = SL; nc.x = cell.x; nc.y = cell.y; nc.z = cell.z; nc.cx = c0[0]; nc.cy = c0[1]; nc.cz = c0[2]; nc.size = sizeC; nc.slot = cell.slot; nc.idx = cell.idx;
       if (lane == 0) { uint32_t m; uint32_t* sw = split_word (p, nc, m); atomicAnd (sw, ~m); }
       if (lane < 8) { gdw[lane] = make_float2 (-1.f, 0.f); if (COLOR) grgb[lane] = make_uchar4 (0, 0, 0, 0); }
       __syncwarp ();
-      if (top->kind[0] == KIND_NEW) { if (lane == 0) top_fallthrough_new (p, f, nc, top->dnew[0], top->uv[0], upd); }
-      else { __threadfence_block (); leaf_visit_warp_bfs (p, f, nc, s_rec[threadIdx.x >> 5], &s_cnt[threadIdx.x >> 5], upd, vis); }
+      if (top->kind[0] == KIND_NEW) { if (lane == 0) rc_cell = top_fallthrough_new (p, f, nc, top->dnew[0], top->uv[0], upd); rc_cell = __shfl_sync (0xffffffffu, rc_cell, 0); }
+      else { __threadfence_block (); rc_cell = leaf_visit_warp_bfs (p, f, nc, s_rec[threadIdx.x >> 5], &s_cnt[threadIdx.x >> 5], upd, vis); }
     }
+    if (lane == 0 && cell_lvl <= 0) cells[ci].rc = rc_cell;              // (read by k_upper_up when coarse levels lie above the supercell)
     if (p.dbg && lane == 0)
     {
       const long long cD = clock64 ();

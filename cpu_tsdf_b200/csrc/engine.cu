@@ -60,6 +60,16 @@ __global__ void k_insert_top_bricks (Params p)
   find_or_insert_brick (p, p.T - 1, x, y, z);
 }
 
+// the static supercell list of grids whose coarse cells lie inside the tier-1 bricks: every root-array node (level Rtop = L - 6)
+__global__ void k_build_superq (Params p, QNode* __restrict__ q, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int nn = 1 << p.Rtop;
+  QNode e; e.x = i / (nn * nn); e.y = (i / nn) % nn; e.z = i % nn; e.slot = -1; e.idx = i; e.kind = KIND_DONE; e.child_base = -1; e.rc = 0;
+  q[i] = e;
+}
+
 // frustum cull of the coarse cells (tsdf_volume_octree.cpp:619-652); planes come from the host
 __global__ void k_cull (Params p, Planes P, int* __restrict__ list, int* __restrict__ count, unsigned char* __restrict__ mask, QNode* __restrict__ q0)
 {
@@ -420,7 +430,10 @@ struct b200tsdf
   Queues Q{}; int q_levels = 0; QNode* q_mem = nullptr; size_t q_mem_cap = 0;
   int* d_blist = nullptr; int* d_bail = nullptr; size_t blist_cap = 0;
   // fused per-cell upper sweeps (coarse cells are the top-tier roots and the block roots are <= 3 levels below)
-  bool cell_path = false; int cell_nl = 0, cell_cap = 0; QNode* d_cellq = nullptr; CellRecord* d_cellrec = nullptr; size_t cellq_cap = 0; CellTop* d_celltop = nullptr; bool top_path = false;
+  // supercell path: sl = level of the tier-1 roots, nup = coarse levels above them (swept by k_upper_*), super_static = number of
+  // supercells when every tier-1 root is one (coarse cells inside the brick), replayable = the frame's launches read only the record
+  int cell_cap = 0; QNode* d_cellq = nullptr; size_t cellq_cap = 0; CellTop* d_celltop = nullptr; QNode* d_superq = nullptr;
+  bool top_path = false, replayable = false; int sl = 0, nup = 0, super_static = 0;
   bool fast_path = false; int force_general = 0;
   bool use_pdl = true;           // programmatic dependent launch between the hot kernels (B200TSDF_PDL=0 turns it off)
   int bd_minb = 6;               // resident CTAs per SM the brick kernel is compiled for (80 registers; tuning knob: B200TSDF_BD_MINB=6|8)
@@ -630,7 +643,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   cudaFree (h->d_bring); if (h->h_bring) cudaFreeHost (h->h_bring);
   for (int i = 0; i < BATCH_SEGS; ++i) if (h->ev_bring[i]) cudaEventDestroy (h->ev_bring[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_half_done[i]) cudaEventDestroy (h->ev_half_done[i]);
-  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop);
+  cudaFree (h->d_frame[0]); cudaFree (h->d_frame[1]); cudaFree (h->q_mem); cudaFree (h->d_blist); cudaFree (h->d_bail); cudaFree (h->d_cellq); cudaFree (h->d_superq); cudaFree (h->d_celltop);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy (h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy (h->ev_consumed[i]); }
   if (h->ev_t0) cudaEventDestroy (h->ev_t0); if (h->ev_t1) cudaEventDestroy (h->ev_t1);
   if (h->ev_k0) cudaEventDestroy (h->ev_k0); if (h->ev_k1) cudaEventDestroy (h->ev_k1);
@@ -729,27 +742,34 @@ int b200tsdf_reset (b200tsdf_t* h)
     for (int i = 0; i < MAX_QLEVELS; ++i) { h->Q.q[i] = nullptr; h->Q.cap[i] = 0; }
     for (int i = 0; i < h->q_levels; ++i) { h->Q.q[i] = h->q_mem + off; h->Q.cap[i] = (int) caps[i]; off += caps[i]; }
     h->Q.n = h->d_count;
-    // per-cell path
-    h->cell_nl = Bl - np.C;
-    h->cell_path = h->fast_path && np.Rtop == np.C && h->cell_nl >= 1 && h->cell_nl <= 3 && !(c.debug_flags & 2);
-    if (h->cell_path)
+    // supercell path (k_celltop_down / k_bricks / k_celltop_up, brick_kernels.cuh): needs tier-1 bricks (T >= 2), whose roots sit
+    // at level SL = L - 6.  Coarse levels above SL are swept by k_upper_*; coarse cells below SL are handled inside the brick.
+    h->sl = np.L - 6;
+    h->nup = std::max (0, h->sl - np.C);
+    h->super_static = 0;
+    h->top_path = h->fast_path && np.T >= 2 && h->sl >= 0 && !(c.debug_flags & 6);
+    if (h->top_path && np.C > h->sl)
     {
-      size_t ncell = (size_t) 1 << (3 * np.C);
-      h->cell_cap = (int) std::min (ncell, (size_t) 16384);
-      size_t stride = h->cell_nl == 1 ? 9 : (h->cell_nl == 2 ? 73 : 585);
-      size_t need = (size_t) h->cell_cap * stride;
+      // every tier-1 root is a supercell; they must be the root-array nodes (T == 2) and fit the per-cell scratch
+      if (np.Rtop != h->sl || h->sl > 4) h->top_path = false;
+      else h->super_static = 1 << (3 * h->sl);
+    }
+    if (h->top_path)
+    {
+      h->cell_cap = 16384;
+      size_t need = (size_t) h->cell_cap * 585;
       if (need > h->cellq_cap)
       {
-        cudaFree (h->d_cellq); cudaFree (h->d_cellrec); cudaFree (h->d_celltop); h->d_cellq = nullptr; h->d_cellrec = nullptr; h->d_celltop = nullptr; h->cellq_cap = 0;
+        cudaFree (h->d_cellq); cudaFree (h->d_celltop); h->d_cellq = nullptr; h->d_celltop = nullptr; h->cellq_cap = 0;
         CK (cudaMalloc (&h->d_cellq, need * sizeof (QNode)));
-        CK (cudaMalloc (&h->d_cellrec, (size_t) h->cell_cap * sizeof (CellRecord)));
         CK (cudaMalloc (&h->d_celltop, (size_t) h->cell_cap * sizeof (CellTop)));
         h->cellq_cap = need;
       }
+      if (h->super_static && !h->d_superq) CK (cudaMalloc (&h->d_superq, 4096 * sizeof (QNode)));
     }
-    h->top_path = h->cell_path && h->cell_nl == 3 && !(c.debug_flags & 4);
+    h->replayable = h->top_path && h->nup == 0;           // (k_upper_* still take the frame by value)
     size_t bl = h->q_levels ? caps[h->q_levels - 1] : 0;
-    if (h->cell_path) bl = std::max (bl, (size_t) h->cell_cap * 512);
+    if (h->top_path) bl = std::max (bl, (size_t) h->cell_cap * 512);
     if (bl > h->blist_cap)
     {
       cudaFree (h->d_blist); cudaFree (h->d_bail); h->d_blist = h->d_bail = nullptr; h->blist_cap = 0;
@@ -793,6 +813,7 @@ int b200tsdf_reset (b200tsdf_t* h)
   CK (cudaMemsetAsync (h->d_stats, 0, ST_TOTAL * sizeof (unsigned long long), s));
   h->kring_pending = 0; h->kring_head = 0;
   if (Rtop < C) k_insert_top_bricks<<<(unsigned) ((root_n + 127) / 128), 128, 0, s>>> (p);
+  if (h->top_path && h->super_static) k_build_superq<<<(h->super_static + 127) / 128, 128, 0, s>>> (p, h->d_superq, h->super_static);
   CK (cudaGetLastError ());
   h->cfg = c;
   h->has_volume = true;
@@ -828,7 +849,7 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
   const int ncells = 1 << (3 * p.C);
   {
     const int cull_blocks = (ncells + 255) / 256;
-    const bool pdl = h->top_path && h->use_pdl;
+    const bool pdl = h->replayable && h->use_pdl;
     if (pdl) CK (launch_pdl (k_front, dim3 (cull_blocks + (npix + 255) / 256), dim3 (256), s, p, d_rec, cull_blocks, h->d_culled, h->d_count, h->Q.q[0], h->d_stats));
     else k_front<<<cull_blocks + (npix + 255) / 256, 256, 0, s>>> (p, d_rec, cull_blocks, h->d_culled, h->d_count, h->fast_path ? h->Q.q[0] : nullptr, h->d_stats);
   }
@@ -842,51 +863,44 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
   if (h->fast_path)
   {
     const int nl = h->q_levels;
-    int* d_bcount = cnt + 9; int* d_bailcount = cnt + 10;
-    Queues Qb = h->Q;
-    int bli = nl - 1;
-    if (h->cell_path)
+    int* d_bcount = cnt + 9;
+    QNode* bq = nullptr;                                   // the queue the block-root entries of k_bricks live in
+    if (h->top_path)
     {
-      const int NL = h->cell_nl;
-      Qb.q[NL] = h->d_cellq; Qb.cap[NL] = (int) std::min (h->cellq_cap, (size_t) 0x7fffffff);
-      bli = NL;
-      if (h->top_path)
-      {
-        auto kd = p.color ? k_celltop_down<true> : k_celltop_down<false>;
-        if (h->use_pdl) CK (launch_pdl (kd, dim3 (h->sm_count * 4), dim3 (TOP_THREADS), s, p, d_rec, (const QNode*) h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats));
-        else kd<<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats);
-      }
-      else if (NL == 1) k_cell_down<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
-      else if (NL == 2) k_cell_down<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
-      else k_cell_down<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, h->Q.q[0], cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_blist, d_bcount, h->d_stats);
+      // coarse levels above the supercells, top-down (none for 2048^3 / 10 m and 512^3 / 3 m)
+      for (int li = 0; li < h->nup; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, 0, h->d_blist, d_bcount, h->d_stats); h->launches++; }
+      QNode* cells = h->super_static ? h->d_superq : h->Q.q[h->nup];
+      const int qslot = h->super_static ? -1 : h->nup;
+      auto kd = p.color ? k_celltop_down<true> : k_celltop_down<false>;
+      if (h->use_pdl) CK (launch_pdl (kd, dim3 (h->sm_count * 4), dim3 (TOP_THREADS), s, p, d_rec, cells, h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats, h->sl, qslot, h->super_static));
+      else kd<<<h->sm_count * 4, TOP_THREADS, 0, s>>> (p, d_rec, cells, h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_blist, (int) h->blist_cap, h->d_stats, h->sl, qslot, h->super_static);
       h->launches++;
+      bq = h->d_cellq;
     }
     else
+    {
       for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
+      bq = h->Q.q[nl - 1];
+    }
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][0], s));
     // the dominant kernel: one warp per interior block root, the brick updated in place
-    (void) d_bailcount;
     {
       auto kb = h->bd_minb == 6 ? (p.color ? k_bricks<true, 6> : k_bricks<false, 6>) : (p.color ? k_bricks<true, 8> : k_bricks<false, 8>);
       const dim3 g (h->sm_count * h->bd_minb), b (BD_WARPS * 32);
-      if (h->top_path && h->use_pdl) CK (launch_pdl (kb, g, b, s, p, (const Params*) h->d_params, d_rec, Qb.q[bli], (const int*) h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3));
-      else kb<<<g, b, 0, s>>> (p, h->d_params, d_rec, Qb.q[bli], h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
+      if (h->top_path && h->use_pdl) CK (launch_pdl (kb, g, b, s, p, (const Params*) h->d_params, d_rec, bq, (const int*) h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3));
+      else kb<<<g, b, 0, s>>> (p, h->d_params, d_rec, bq, h->d_blist, (int) h->blist_cap, h->d_count, h->d_stats, p.L - 3);
     }
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][1], s));
     h->launches++;
-    if (h->cell_path)
+    if (h->top_path)
     {
-      const int NL = h->cell_nl;
-      if (h->top_path)
-      {
-        auto ku = p.color ? k_celltop_up<true> : k_celltop_up<false>;
-        if (h->use_pdl) CK (launch_pdl (ku, dim3 (h->sm_count), dim3 (128), s, p, d_rec, (const QNode*) h->Q.q[0], (const int*) h->d_count, (const QNode*) h->d_cellq, (const CellTop*) h->d_celltop, h->cell_cap, h->d_stats));
-        else ku<<<h->sm_count, 128, 0, s>>> (p, d_rec, h->Q.q[0], h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats);
-      }
-      else if (NL == 1) k_cell_up<1><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
-      else if (NL == 2) k_cell_up<2><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
-      else k_cell_up<3><<<148 * 4, CELL_THREADS, 0, s>>> (p, f, cnt, h->d_cellq, h->d_cellrec, h->cell_cap, h->d_stats);
+      QNode* cells = h->super_static ? h->d_superq : h->Q.q[h->nup];
+      const int qslot = h->super_static ? -1 : h->nup;
+      auto ku = p.color ? k_celltop_up<true> : k_celltop_up<false>;
+      if (h->use_pdl) CK (launch_pdl (ku, dim3 (h->sm_count), dim3 (128), s, p, d_rec, cells, (const int*) h->d_count, (const QNode*) h->d_cellq, (const CellTop*) h->d_celltop, h->cell_cap, h->d_stats, h->sl, qslot, h->super_static));
+      else ku<<<h->sm_count, 128, 0, s>>> (p, d_rec, cells, h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats, h->sl, qslot, h->super_static);
       h->launches++;
+      for (int li = h->nup - 1; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
     }
     else
       for (int li = nl - 2; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
@@ -1035,7 +1049,7 @@ int b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_
   for (int done = 0; done < n;)
   {
     const int m = std::min (HALF, n - done);
-    if (!h->top_path)
+    if (!h->replayable)
     {
       // grid shapes whose launches are not replayable: frame by frame
       for (int i = 0; i < m; ++i)

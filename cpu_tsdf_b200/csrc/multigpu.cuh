@@ -191,7 +191,7 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
                         : (const void*) (h->d_rows_full[s] + (size_t) (c0 + i) * frame16);
     const size_t f_stride = nr == 1 ? stride : 16; const int f_xyz = nr == 1 ? xyz_off : 0, f_rgba = nr == 1 ? rgba_off : out_rgba;
     // the chunk's frame records travel on the copy stream ahead of its frames
-    if (h->top_path) { if (int rc = batch_records (h, m, ptrs, f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) c0, cs)) return rc; }
+    if (h->replayable) { if (int rc = batch_records (h, m, ptrs, f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) c0, cs)) return rc; }
     for (int i = c0; i < c0 + m; ++i)
     {
       if (!rows[i] && slice_raw) return h->fail (B200TSDF_EINVAL, "null row slice in batch");
@@ -222,7 +222,7 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
       CK (cudaEventRecord (ready, gs));
     }
     CK (cudaStreamWaitEvent (h->stream, ready, 0));
-    if (h->top_path) { if (int rc = batch_launch (h, m)) return rc; }
+    if (h->replayable) { if (int rc = batch_launch (h, m)) return rc; }
     else
       for (int i = 0; i < m; ++i)
         if (int rc = integrate_on_device (h, (const unsigned char*) ptrs[i], f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) (c0 + i))) return rc;
