@@ -17,6 +17,7 @@
 // handed to the general depth-first routine update_voxel_dfs for that subtree only.
 #pragma once
 #include "tsdf_core.cuh"
+#include "obs_fast.cuh"
 
 namespace b2 {
 
@@ -477,6 +478,9 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
   const float sizeC = level_size (p, SL);
   const float off1 = sizeC * 0.25f;
   const double thr[4] = { near_threshold (sizeC), near_threshold (sizeC * 0.5f), near_threshold (sizeC * 0.25f), near_threshold (sizeC * 0.125f) };
+  const float thrf[4] = { float_at_least (thr[0]), float_at_least (thr[1]), float_at_least (thr[2]), float_at_least (thr[3]) };
+  const bool have_bgra = COLOR && p.color && f.rgba_off >= 0;
+  FrameHot F; F.pts = f.pts + f.xyz_off + 8; F.stride = f.stride; F.coff = have_bgra ? f.rgba_off - (f.xyz_off + 8) : 0;
   for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
   {
     __syncthreads ();
@@ -494,10 +498,12 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
       int k, j; top_kj (n, k, j);
       float c[3];
       if (k == 0) { c[0] = c0[0]; c[1] = c0[1]; c[2] = c0[2]; } else path_center (c0, off1, k, j, c);
-      Obs o = observe_thr (p, f, c[0], c[1], c[2], thr[k]);
-      S.o_dnew[n] = o.d_new; S.o_uv[n] = o.u | (o.v << 16);
-      S.o_bgra[n] = (COLOR && o.valid && f.rgba_off >= 0) ? *reinterpret_cast<const uint32_t*> (frame_bgr (f, o.u, o.v)) : 0u;
-      S.o_flags[n] = (unsigned char) ((o.valid ? 1 : 0) | (o.near_ ? 2 : 0));
+      float vg[3];
+      pcl_transform_point_f (f.tinv, c[0], c[1], c[2], vg);                           // hpp:145
+      const ObsF o = observe_fast<COLOR> (p, F, vg[0], vg[1], vg[2]);
+      S.o_dnew[n] = o.d_new; S.o_uv[n] = o.uv;
+      S.o_bgra[n] = (have_bgra && o.valid) ? o.bgra : 0u;
+      S.o_flags[n] = (unsigned char) ((o.valid ? 1 : 0) | ((o.valid && fabsf (o.d_new) < thrf[k]) ? 2 : 0));
       S.kind[n] = KIND_DONE; S.rc[n] = 0; S.dirty[n] = 0;
     }
     // ---- the supercell itself (its state lives in the root arrays or in the tier above; none when it is virtual) ----

@@ -115,15 +115,10 @@ def sharded_stream(res, size, pool, nframes, total_orbit, max_cell, dist, rank, 
     # one untimed batch first: NCCL channel set-up, graph capture and the staging buffers are one-time costs
     v.integrateBatchRows([rows[i].data_ptr() for i in range(min(8, len(rows)))], H, W, 32, poses[:min(8, len(rows))], rgba_off=16)
     v.sync()
-    if full is not None and world > 1:
-        pass
     if world > 1 and (render_every or mesh):
         if full is not None:
             full.reset()
         v.gatherVolume(full, 0)
-    v.reset(); 
-    if full is not None:
-        full.reset()
     barrier()
     t0 = time.perf_counter()
     v.profile_begin()
