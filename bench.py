@@ -363,6 +363,8 @@ def main():
                      "load": f"{os.cpu_count()} busy-loop processes (one per host core) during the batched device-resident leg"}
 
     # ---- end-to-end leg (host buffers, public API) ---------------------------------------------
+    host_pack = os.environ.get("B200TSDF_HOST_PACK", "1") != "0"
+    pack_threads = int(os.environ.get("B200TSDF_PACK_THREADS", "0")) or max(1, min(16, (os.cpu_count() or 1) // (2 * world)))
     for _ in range(max(1, args.warmup // 2)):
         step_host(k); k += FRAMES_PER_STEP
     barrier()
@@ -436,8 +438,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": int(prof_e.h2d_bytes // args.steps), "d2h_bytes_per_step": int(prof_e.d2h_bytes // args.steps),
                     "nvlink_bytes_per_step": int(prof_e.nvlink_bytes // args.steps),
-                    "path": "b200tsdf_integrate_batch_rows: each rank uploads rows [%d, %d) of every frame from pinned host memory, packs to 16 B pixels, "
-                            "NCCL all-gather over NVLink, one graph launch per 32 frames" % (row0, row1),
+                    "path": ("b200tsdf_integrate_batch_rows: host threads pack each rank's rows [%d, %d) of every 32 B/point frame to 16 B pixels into pinned "
+                             "staging (bit-preserving), only those cross PCIe; NCCL all-gather over NVLink at N>1; one graph launch per chunk of 8 frames"
+                             if host_pack else
+                             "b200tsdf_integrate_batch_rows: each rank uploads rows [%d, %d) of every frame from pinned host memory, packs to 16 B pixels on the device, "
+                             "NCCL all-gather over NVLink, one graph launch per chunk of 8 frames") % (row0, row1),
+                    "host_pack": {"enabled": host_pack, "threads": pack_threads if host_pack else 0,
+                                  "input_bytes_per_step": int(FRAMES_PER_STEP * (row1 - row0) * W * stride)},
                     "timing": "max(CUDA events on the engine stream, host wall clock) over ranks", "host_affinity": affinity},
             "gpu_launches": int(prof.total_launches),
             "graph_launches": int(prof.graph_launches),

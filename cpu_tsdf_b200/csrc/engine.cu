@@ -11,6 +11,7 @@
 #include "brick_direct.cuh"
 #include "organize.cuh"
 #include "mesh_sort.h"
+#include "host_pack.h"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -457,6 +458,11 @@ struct b200tsdf
   size_t rows_raw_cap = 0, rows_full_cap = 0; int rows_set = 0; bool rows_used[2] = { false, false };
   int rows_chunk = 8;            // frames per upload/fuse pipeline stage of b200tsdf_integrate_batch_rows (B200TSDF_ROWS_CHUNK=2..32)
   cudaEvent_t ev_rows_up[2][16] = {}, ev_rows_ready[2][16] = {}, ev_rows_done[2] = { nullptr, nullptr };
+  // host packing of the uploaded rows (host_pack.h): pinned staging per buffer set, the pool is created on first use
+  int host_pack = 1;             // B200TSDF_HOST_PACK=0: upload the caller's points as they are and pack on the device
+  int pack_threads = 0;          // B200TSDF_PACK_THREADS (0 = min (16, hardware threads / (2 ranks)))
+  b2host::PackPool* pack_pool = nullptr;
+  unsigned char* h_pack[2] = { nullptr, nullptr }; size_t pack_cap = 0;
   long long nvlink_bytes = 0, prof_nvlink0 = 0;
   int launches_per_frame = 0; long long graph_launches = 0, prof_graph0 = 0;
   // measurement
@@ -579,6 +585,8 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   h->device = h->cfg_pending.device;
   if (const char* e = std::getenv ("B200TSDF_PDL")) h->use_pdl = std::atoi (e) != 0;
   if (const char* e = std::getenv ("B200TSDF_ROWS_CHUNK")) { const int v = std::atoi (e); if (v >= 2 && v <= 32) h->rows_chunk = v; }
+  if (const char* e = std::getenv ("B200TSDF_HOST_PACK")) h->host_pack = std::atoi (e) != 0;
+  if (const char* e = std::getenv ("B200TSDF_PACK_THREADS")) { const int v = std::atoi (e); if (v >= 1 && v <= 256) h->pack_threads = v; }
   if (const char* e = std::getenv ("B200TSDF_BD_MINB")) { const int v = std::atoi (e); if (v == 6 || v == 8) h->bd_minb = v; }
   if (h->device < 0 || h->device >= ndev) { delete h; return B200TSDF_EINVAL; }
   bool ok = cudaSetDevice (h->device) == cudaSuccess
@@ -634,9 +642,11 @@ void b200tsdf_destroy (b200tsdf_t* h)
   for (int i = 0; i < 2; ++i) if (h->ev_ring[i]) cudaEventDestroy (h->ev_ring[i]);
   drop_batch_graphs (h);
   comm_release (h);
+  delete h->pack_pool; h->pack_pool = nullptr;
   for (int i = 0; i < 2; ++i)
   {
     cudaFree (h->d_rows_raw[i]); cudaFree (h->d_rows_full[i]);
+    if (h->h_pack[i]) cudaFreeHost (h->h_pack[i]);
     for (int k = 0; k < 16; ++k) { if (h->ev_rows_ready[i][k]) cudaEventDestroy (h->ev_rows_ready[i][k]); if (h->ev_rows_up[i][k]) cudaEventDestroy (h->ev_rows_up[i][k]); }
     if (h->ev_rows_done[i]) cudaEventDestroy (h->ev_rows_done[i]);
   }

@@ -160,19 +160,32 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   const int row0 = std::min (height, rk * per), row1 = std::min (height, (rk + 1) * per);
   const size_t slice_raw = (size_t) (row1 - row0) * width * stride;
   const size_t slice16 = (size_t) per * width * 16, frame16 = slice16 * nr;
+  // host packing (host_pack.h): the caller's rows are packed to 16-byte pixels by host threads into pinned staging and only
+  // those cross PCIe; without it the points are uploaded as they are (and packed on the device when there is a gather)
+  const bool hpack = h->host_pack && stride > 16;
   // two buffer sets, used alternately: set s is rewritten only after the batch that read it two calls ago has been fused
   const int s = h->rows_set;
-  const size_t need_raw = (size_t) HALF * per * width * stride, need_full = (size_t) HALF * frame16;
-  if (need_raw > h->rows_raw_cap || need_full > h->rows_full_cap)
+  const size_t need_raw = hpack ? 0 : (size_t) HALF * per * width * stride, need_full = (size_t) HALF * frame16, need_pack = hpack ? (size_t) HALF * slice16 : 0;
+  if (need_raw > h->rows_raw_cap || need_full > h->rows_full_cap || need_pack > h->pack_cap)
   {
-    CK (cudaStreamSynchronize (h->stream)); CK (cudaStreamSynchronize (h->copy_stream));
+    CK (cudaStreamSynchronize (h->stream)); CK (cudaStreamSynchronize (h->copy_stream)); CK (cudaStreamSynchronize (h->gather_stream));
     for (int k = 0; k < 2; ++k)
     {
       cudaFree (h->d_rows_raw[k]); cudaFree (h->d_rows_full[k]); h->d_rows_raw[k] = h->d_rows_full[k] = nullptr;
-      CK (cudaMalloc (&h->d_rows_raw[k], need_raw)); CK (cudaMalloc (&h->d_rows_full[k], need_full));
+      if (h->h_pack[k]) { cudaFreeHost (h->h_pack[k]); h->h_pack[k] = nullptr; }
+      h->rows_raw_cap = h->rows_full_cap = h->pack_cap = 0;
+      if (need_raw) CK (cudaMalloc (&h->d_rows_raw[k], need_raw));
+      CK (cudaMalloc (&h->d_rows_full[k], need_full));
+      if (need_pack) CK (cudaHostAlloc (&h->h_pack[k], need_pack, cudaHostAllocDefault));
       h->rows_used[k] = false;
     }
-    h->rows_raw_cap = need_raw; h->rows_full_cap = need_full;
+    h->rows_raw_cap = need_raw; h->rows_full_cap = need_full; h->pack_cap = need_pack;
+  }
+  if (hpack && !h->pack_pool)
+  {
+    int t = h->pack_threads;
+    if (t <= 0) { const int hw = (int) std::thread::hardware_concurrency (); t = std::max (1, std::min (16, hw / (2 * nr))); }
+    h->pack_pool = new b2host::PackPool (t);
   }
   // three-stage pipeline, ROWS_CHUNK frames per stage: the copy stream only uploads (the copy engine never waits for a
   // kernel), the gather stream packs and all-gathers, the compute stream fuses.  Grid shapes without replayable launches
@@ -185,30 +198,56 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   for (int c0 = 0; c0 < n; c0 += ROWS_CHUNK)
   {
     const int m = std::min (ROWS_CHUNK, n - c0);
+    const bool raw_in_place = nr == 1 && !hpack;           // one rank, no host packing: fused where the points landed
     const void* ptrs[HALF];
     for (int i = 0; i < m; ++i)
-      ptrs[i] = nr == 1 ? (const void*) (h->d_rows_raw[s] + (size_t) (c0 + i) * per * width * stride)      // one rank: fused where it landed
-                        : (const void*) (h->d_rows_full[s] + (size_t) (c0 + i) * frame16);
-    const size_t f_stride = nr == 1 ? stride : 16; const int f_xyz = nr == 1 ? xyz_off : 0, f_rgba = nr == 1 ? rgba_off : out_rgba;
+      ptrs[i] = raw_in_place ? (const void*) (h->d_rows_raw[s] + (size_t) (c0 + i) * per * width * stride)
+                             : (const void*) (h->d_rows_full[s] + (size_t) (c0 + i) * frame16);
+    const size_t f_stride = raw_in_place ? stride : 16; const int f_xyz = raw_in_place ? xyz_off : 0, f_rgba = raw_in_place ? rgba_off : out_rgba;
+    for (int i = c0; i < c0 + m; ++i) if (!rows[i] && slice_raw) return h->fail (B200TSDF_EINVAL, "null row slice in batch");
     // the chunk's frame records travel on the copy stream ahead of its frames
     if (h->replayable) { if (int rc = batch_records (h, m, ptrs, f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) c0, cs)) return rc; }
-    for (int i = c0; i < c0 + m; ++i)
+    if (hpack)
     {
-      if (!rows[i] && slice_raw) return h->fail (B200TSDF_EINVAL, "null row slice in batch");
-      if (slice_raw) CK (cudaMemcpyAsync (h->d_rows_raw[s] + (size_t) i * per * width * stride, rows[i], slice_raw, cudaMemcpyHostToDevice, cs));
-      h->h2d_bytes += (long long) slice_raw;
+      // the staging of this chunk is rewritten only after the upload that read it two calls ago has left it
+      if (h->rows_used[s]) CK (cudaEventSynchronize (h->ev_rows_up[s][c0 / ROWS_CHUNK]));
+      if (npts)
+      {
+        const int T = h->pack_pool->threads ();
+        const int nb = std::max (1, std::min ((4 * T + m - 1) / m, npts / 4096));         // row blocks per frame
+        unsigned char* stage = h->h_pack[s];
+        const int pack_rgba = h->p.color ? rgba_off : -1;
+        std::function<void (int)> job = [&] (int j)
+        {
+          const int i = c0 + j / nb, b = j % nb;
+          const size_t p0 = (size_t) npts * b / nb, p1 = (size_t) npts * (b + 1) / nb;
+          b2host::pack_points16 (static_cast<const unsigned char*> (rows[i]) + p0 * stride, stride, xyz_off, pack_rgba, p1 - p0, stage + (size_t) i * slice16 + p0 * 16);
+        };
+        h->pack_pool->run (m * nb, job);
+        if (nr == 1) CK (cudaMemcpyAsync (h->d_rows_full[s] + (size_t) c0 * frame16, stage + (size_t) c0 * slice16, (size_t) m * slice16, cudaMemcpyHostToDevice, cs));
+        else
+          for (int i = c0; i < c0 + m; ++i)
+            CK (cudaMemcpyAsync (h->d_rows_full[s] + (size_t) i * frame16 + (size_t) rk * slice16, stage + (size_t) i * slice16, (size_t) npts * 16, cudaMemcpyHostToDevice, cs));
+        h->h2d_bytes += (long long) m * npts * 16;
+      }
     }
+    else
+      for (int i = c0; i < c0 + m; ++i)
+      {
+        if (slice_raw) CK (cudaMemcpyAsync (h->d_rows_raw[s] + (size_t) i * per * width * stride, rows[i], slice_raw, cudaMemcpyHostToDevice, cs));
+        h->h2d_bytes += (long long) slice_raw;
+      }
     cudaEvent_t up = h->ev_rows_up[s][c0 / ROWS_CHUNK], ready = up;
     CK (cudaEventRecord (up, cs));
     if (nr > 1)
     {
       CK (cudaStreamWaitEvent (gs, up, 0));
-      for (int i = c0; i < c0 + m && npts; ++i)
+      for (int i = c0; i < c0 + m && npts && !hpack; ++i)
       {
         uint4* dst = reinterpret_cast<uint4*> (h->d_rows_full[s] + (size_t) i * frame16 + (size_t) rk * slice16);
         k_pack_rows<<<(npts + 255) / 256, 256, 0, gs>>> (h->d_rows_raw[s] + (size_t) i * per * width * stride, stride, xyz_off, h->p.color ? rgba_off : -1, npts, dst);
       }
-      h->launches += m;
+      if (!hpack) h->launches += m;
       // one grouped launch: m in-place all-gathers, frame i's slices land row-major in its full 16-byte image
       NK (a.GroupStart ());
       for (int i = c0; i < c0 + m; ++i)

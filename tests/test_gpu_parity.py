@@ -383,6 +383,28 @@ def test_batch_graph_replay_matches_the_oracle_and_frame_by_frame():
     assert_same_nodes(o2.dump_nodes(), e2.download_nodes())
 
 
+@pytest.mark.parametrize("host_pack", ["1", "0"])
+def test_batch_rows_from_host_buffers_one_gpu(host_pack, monkeypatch):
+    """b200tsdf_integrate_batch_rows on one GPU (the end-to-end path of bench.py): HOST rows in, packed to 16-byte pixels by
+    the host thread pool (B200TSDF_HOST_PACK=1, the default; 3 threads here so the fork/join is exercised) or uploaded as
+    they are (=0); either way the volume is the oracle's, bit for bit.  Batches of 9 and 4 frames: chunks of 8 + 1, then a
+    short batch on the second buffer set, then the first set again."""
+    monkeypatch.setenv("B200TSDF_HOST_PACK", host_pack)
+    monkeypatch.setenv("B200TSDF_PACK_THREADS", "3")
+    o, e = pair(CFG_512, 18, integrate_color=1)
+    fs = list(frames(synth.S1, 17, stride=5, color=True, noise_seed=33))
+    host = [np.ascontiguousarray(c) for _, c in fs]
+    for pose, cloud in fs:
+        o.integrate(cloud, pose)
+    H, W = host[0].shape[:2]
+    assert e.rowSlice(H) == (0, H)
+    for lo, hi in ((0, 9), (9, 13), (13, 17)):
+        e.integrateBatchRows([c.ctypes.data for c in host[lo:hi]], H, W, 32, [p for p, _ in fs[lo:hi]], rgba_off=16)
+    e.sync()
+    assert_same_nodes(o.dump_nodes(), e.download_nodes(), rgb=True)
+    assert e.stats().n_updates == o.stats().n_add_observation
+
+
 def test_get_tsdf_value_direct_entry_point():
     """b200tsdf_interpolate = getTSDFValue / interpolateTrilinearly (cpp:454-541): value bits, NaN on the border layer and outside,
     and the in/out `valid` flag, against the oracle (itself pinned to the reference for this call in tests/test_ref_pin.py)."""
