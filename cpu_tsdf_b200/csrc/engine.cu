@@ -455,14 +455,15 @@ struct b200tsdf
   // multi-GPU (multigpu.cuh): NCCL communicator (opaque here), row-sliced uploads
   void* comm = nullptr; int comm_rank = 0, comm_size = 1;
   unsigned char* d_rows_raw[2] = { nullptr, nullptr }; unsigned char* d_rows_full[2] = { nullptr, nullptr };
-  size_t rows_raw_cap = 0, rows_full_cap = 0; int rows_set = 0; bool rows_used[2] = { false, false };
-  int rows_chunk = 8;            // frames per upload/fuse pipeline stage of b200tsdf_integrate_batch_rows (B200TSDF_ROWS_CHUNK=2..32)
-  cudaEvent_t ev_rows_up[2][16] = {}, ev_rows_ready[2][16] = {}, ev_rows_done[2] = { nullptr, nullptr };
+  size_t rows_raw_cap = 0, rows_full_cap = 0; int rows_set = 0; bool rows_used[2] = { false, false }; int rows_last_up[2] = { 0, 0 };
+  int rows_chunk = 0;            // frames per upload/fuse pipeline stage of b200tsdf_integrate_batch_rows (B200TSDF_ROWS_CHUNK=1..32; 0: 1 or 2 with host packing, else 8)
+  cudaEvent_t ev_rows_up[2][32] = {}, ev_rows_ready[2][32] = {}, ev_rows_done[2] = { nullptr, nullptr };
   // host packing of the uploaded rows (host_pack.h): pinned staging per buffer set, the pool is created on first use
-  int host_pack = 1;             // B200TSDF_HOST_PACK=0: upload the caller's points as they are and pack on the device
+  int host_pack = -1;            // B200TSDF_HOST_PACK: 1 pack on the host, 0 upload the caller's points as they are (packed on the device when gathered); -1 by rank count
   int pack_threads = 0;          // B200TSDF_PACK_THREADS (0 = min (16, hardware threads / (2 ranks)))
   b2host::PackPool* pack_pool = nullptr;
   unsigned char* h_pack[2] = { nullptr, nullptr }; size_t pack_cap = 0;
+  unsigned char* h_fpack[2] = { nullptr, nullptr };   // the same for the frame-at-a-time upload (d_frame[]), frame_cap bytes each
   long long nvlink_bytes = 0, prof_nvlink0 = 0;
   int launches_per_frame = 0; long long graph_launches = 0, prof_graph0 = 0;
   // measurement
@@ -584,8 +585,8 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   if (cfg) h->cfg_pending = *cfg; else b200tsdf_default_config (&h->cfg_pending);
   h->device = h->cfg_pending.device;
   if (const char* e = std::getenv ("B200TSDF_PDL")) h->use_pdl = std::atoi (e) != 0;
-  if (const char* e = std::getenv ("B200TSDF_ROWS_CHUNK")) { const int v = std::atoi (e); if (v >= 2 && v <= 32) h->rows_chunk = v; }
-  if (const char* e = std::getenv ("B200TSDF_HOST_PACK")) h->host_pack = std::atoi (e) != 0;
+  if (const char* e = std::getenv ("B200TSDF_ROWS_CHUNK")) { const int v = std::atoi (e); if (v >= 1 && v <= 32) h->rows_chunk = v; }
+  if (const char* e = std::getenv ("B200TSDF_HOST_PACK")) h->host_pack = std::atoi (e) != 0 ? 1 : 0;
   if (const char* e = std::getenv ("B200TSDF_PACK_THREADS")) { const int v = std::atoi (e); if (v >= 1 && v <= 256) h->pack_threads = v; }
   if (const char* e = std::getenv ("B200TSDF_BD_MINB")) { const int v = std::atoi (e); if (v == 6 || v == 8) h->bd_minb = v; }
   if (h->device < 0 || h->device >= ndev) { delete h; return B200TSDF_EINVAL; }
@@ -615,8 +616,8 @@ int b200tsdf_create (const b200tsdf_config* cfg, b200tsdf_t** out)
   ok = ok && cudaEventCreate (&h->ev_t0) == cudaSuccess && cudaEventCreate (&h->ev_t1) == cudaSuccess
           && cudaEventCreate (&h->ev_k0) == cudaSuccess && cudaEventCreate (&h->ev_k1) == cudaSuccess
           && cudaEventCreate (&h->ev_p0) == cudaSuccess && cudaEventCreate (&h->ev_p1) == cudaSuccess;
-  for (int i = 0; ok && i < 32; ++i) ok = cudaEventCreateWithFlags (&h->ev_rows_ready[i / 16][i % 16], cudaEventDisableTiming) == cudaSuccess
-                                          && cudaEventCreateWithFlags (&h->ev_rows_up[i / 16][i % 16], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 64; ++i) ok = cudaEventCreateWithFlags (&h->ev_rows_ready[i / 32][i % 32], cudaEventDisableTiming) == cudaSuccess
+                                          && cudaEventCreateWithFlags (&h->ev_rows_up[i / 32][i % 32], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < KRING; ++i)
     ok = cudaEventCreate (&h->kring[i][0]) == cudaSuccess && cudaEventCreate (&h->kring[i][1]) == cudaSuccess;
   if (ok) *h->h_err = 0;
@@ -647,7 +648,8 @@ void b200tsdf_destroy (b200tsdf_t* h)
   {
     cudaFree (h->d_rows_raw[i]); cudaFree (h->d_rows_full[i]);
     if (h->h_pack[i]) cudaFreeHost (h->h_pack[i]);
-    for (int k = 0; k < 16; ++k) { if (h->ev_rows_ready[i][k]) cudaEventDestroy (h->ev_rows_ready[i][k]); if (h->ev_rows_up[i][k]) cudaEventDestroy (h->ev_rows_up[i][k]); }
+    if (h->h_fpack[i]) cudaFreeHost (h->h_fpack[i]);
+    for (int k = 0; k < 32; ++k) { if (h->ev_rows_ready[i][k]) cudaEventDestroy (h->ev_rows_ready[i][k]); if (h->ev_rows_up[i][k]) cudaEventDestroy (h->ev_rows_up[i][k]); }
     if (h->ev_rows_done[i]) cudaEventDestroy (h->ev_rows_done[i]);
   }
   cudaFree (h->d_bring); if (h->h_bring) cudaFreeHost (h->h_bring);
@@ -1075,6 +1077,39 @@ int b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_
   return B200TSDF_OK;
 }
 
+// the host threads that pack uploaded points to 16-byte pixels (host_pack.h), created on first use
+static void ensure_pack_pool (b200tsdf* h, int nr)
+{
+  if (h->pack_pool) return;
+  int t = h->pack_threads;
+  if (t <= 0) { const int hw = (int) std::thread::hardware_concurrency (); t = std::max (1, std::min (16, hw / (2 * nr))); }
+  // B200TSDF_PACK_CPUS: "local" = the cores next to this GPU's PCIe root (sysfs local_cpulist), or an explicit cpulist
+  std::string cpus;
+  if (const char* e = std::getenv ("B200TSDF_PACK_CPUS"))
+  {
+    cpus = e;
+    if (cpus == "local")
+    {
+      cpus.clear ();
+      char bus[32] = {};
+      if (cudaDeviceGetPCIBusId (bus, sizeof (bus), h->device) == cudaSuccess)
+      {
+        for (char* c = bus; *c; ++c) *c = (char) std::tolower ((unsigned char) *c);
+        if (FILE* f = std::fopen ((std::string ("/sys/bus/pci/devices/") + bus + "/local_cpulist").c_str (), "r"))
+        {
+          char line[512] = {};
+          if (std::fgets (line, sizeof (line), f)) { cpus = line; while (!cpus.empty () && (cpus.back () == '\n' || cpus.back () == ' ')) cpus.pop_back (); }
+          std::fclose (f);
+        }
+      }
+    }
+  }
+  h->pack_pool = new b2host::PackPool (t, cpus);
+}
+
+// is the upload of `stride`-byte points packed on the host?  (-1: by rank count, see b200tsdf_integrate_batch_rows)
+static bool host_pack_wanted (const b200tsdf* h, size_t stride, int nr) { return (h->host_pack < 0 ? nr <= 2 : h->host_pack != 0) && stride > 16; }
+
 static int integrate_host (b200tsdf* h, const void* points, size_t stride, int xyz_off, int rgba_off,
                            int width, int height, const double* pose, bool wait_copy)
 {
@@ -1082,30 +1117,56 @@ static int integrate_host (b200tsdf* h, const void* points, size_t stride, int x
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
   if (int rc = check_cloud_layout (h, stride, xyz_off, rgba_off, width, height)) return rc;
   cudaSetDevice (h->device);
-  size_t bytes = (size_t) width * height * stride;
-  if (bytes > h->frame_cap)
+  // points wider than 16 bytes are packed to {x, y, z, bgra} by the host threads into pinned staging (also the way out of a
+  // pageable pcl cloud at full PCIe speed); the caller's buffer is free again when this call returns
+  const bool hpack = host_pack_wanted (h, stride, h->comm ? h->comm_size : 1);
+  const size_t npts = (size_t) width * height;
+  const size_t bytes = hpack ? npts * 16 : npts * stride;
+  if (bytes > h->frame_cap || (hpack && !h->h_fpack[0]))
   {
     CK (cudaStreamSynchronize (h->stream)); CK (cudaStreamSynchronize (h->copy_stream));
-    for (int i = 0; i < 2; ++i) { cudaFree (h->d_frame[i]); h->d_frame[i] = nullptr; CK (cudaMalloc (&h->d_frame[i], bytes)); }
-    h->frame_cap = bytes;
+    const size_t cap = std::max (bytes, h->frame_cap);
+    for (int i = 0; i < 2; ++i)
+    {
+      cudaFree (h->d_frame[i]); h->d_frame[i] = nullptr; CK (cudaMalloc (&h->d_frame[i], cap));
+      if (h->h_fpack[i]) { cudaFreeHost (h->h_fpack[i]); h->h_fpack[i] = nullptr; }
+      if (hpack) CK (cudaHostAlloc (&h->h_fpack[i], cap, cudaHostAllocDefault));
+    }
+    h->frame_cap = cap;
     h->frame_no = 0;
   }
   // double-buffered upload on the copy stream: frame i+1 crosses PCIe while frame i is fused
   int b = (int) (h->frame_no & 1);
   if (h->frame_no >= 2)
   {
-    CK (cudaEventSynchronize (h->ev_copied[b]));           // the upload of frame i-2 has left the caller's buffer (the documented contract)
+    CK (cudaEventSynchronize (h->ev_copied[b]));           // the upload of frame i-2 has left the caller's buffer / the staging (the documented contract)
     CK (cudaStreamWaitEvent (h->copy_stream, h->ev_consumed[b], 0));
   }
-  CK (cudaMemcpyAsync (h->d_frame[b], points, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  const void* src = points;
+  size_t f_stride = stride; int f_xyz = xyz_off, f_rgba = rgba_off;
+  if (hpack)
+  {
+    ensure_pack_pool (h, h->comm ? h->comm_size : 1);
+    const int nb = (int) std::max<size_t> (1, std::min<size_t> (4 * (size_t) h->pack_pool->threads (), npts / 4096));
+    const int pack_rgba = h->p.color ? rgba_off : -1;
+    unsigned char* stage = h->h_fpack[b];
+    std::function<void (int)> job = [&] (int j)
+    {
+      const size_t p0 = npts * (size_t) j / nb, p1 = npts * (size_t) (j + 1) / nb;
+      b2host::pack_points16 (static_cast<const unsigned char*> (points) + p0 * stride, stride, xyz_off, pack_rgba, p1 - p0, stage + p0 * 16);
+    };
+    h->pack_pool->run (nb, job);
+    src = stage; f_stride = 16; f_xyz = 0; f_rgba = (h->p.color && rgba_off >= 0) ? 12 : -1;
+  }
+  CK (cudaMemcpyAsync (h->d_frame[b], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
   h->h2d_bytes += (long long) bytes;
   CK (cudaEventRecord (h->ev_copied[b], h->copy_stream));
   CK (cudaStreamWaitEvent (h->stream, h->ev_copied[b], 0));
-  int rc = integrate_on_device (h, h->d_frame[b], stride, xyz_off, rgba_off, width, height, pose);
+  int rc = integrate_on_device (h, h->d_frame[b], f_stride, f_xyz, f_rgba, width, height, pose);
   if (rc) return rc;
   CK (cudaEventRecord (h->ev_consumed[b], h->stream));
   h->frame_no++;
-  if (wait_copy) CK (cudaEventSynchronize (h->ev_copied[b]));       // the caller may reuse its buffer now
+  if (wait_copy && !hpack) CK (cudaEventSynchronize (h->ev_copied[b]));       // the caller may reuse its buffer now
   return B200TSDF_OK;
 }
 

@@ -9,6 +9,10 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <pthread.h>
+#include <sched.h>
+#include <string>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 #if defined(__SSE2__)
@@ -18,13 +22,32 @@
 namespace b2host
 {
 
-// fork/join over job indices: run (n, fn) calls fn (j) for every j in [0, n) on the pool's threads and on the calling thread
+// fork/join over job indices: fn (j) is called for every j in [0, n), in ascending order of j, on the pool's threads and on the
+// calling thread
 class PackPool
 {
 public:
-  explicit PackPool (int threads)
+  // cpus: optional Linux cpulist ("0-31,64-95") the pool's own threads are confined to (the caller's thread is left alone)
+  explicit PackPool (int threads, const std::string& cpus = std::string ())
   {
-    for (int i = 0; i < threads - 1; ++i) th_.emplace_back ([this] { worker (); });     // the caller is the last worker
+    cpu_set_t set; CPU_ZERO (&set);
+    bool confine = false;
+    for (size_t at = 0; at < cpus.size ();)
+    {
+      char* e = nullptr;
+      const long lo = std::strtol (cpus.c_str () + at, &e, 10);
+      if (e == cpus.c_str () + at) break;
+      long hi = lo;
+      if (*e == '-') { const char* b = e + 1; hi = std::strtol (b, &e, 10); if (e == b) break; }
+      for (long c = lo; c <= hi && c < CPU_SETSIZE; ++c) if (c >= 0) { CPU_SET ((int) c, &set); confine = true; }
+      at = (size_t) (e - cpus.c_str ());
+      if (at < cpus.size () && cpus[at] == ',') ++at; else break;
+    }
+    for (int i = 0; i < threads - 1; ++i)
+    {
+      th_.emplace_back ([this] { worker (); });                                         // the caller is the last worker
+      if (confine) pthread_setaffinity_np (th_.back ().native_handle (), sizeof (set), &set);
+    }
   }
   ~PackPool ()
   {
@@ -36,7 +59,9 @@ public:
   PackPool& operator= (const PackPool&) = delete;
   int threads () const { return (int) th_.size () + 1; }
 
-  void run (int njobs, const std::function<void (int)>& fn)
+  // begin () hands the jobs to the pool and returns; help () runs one pending job on the calling thread (false: none left to
+  // take); end () drains on the calling thread and returns once every job has been run and no worker still holds `fn`.
+  void begin (int njobs, const std::function<void (int)>& fn)
   {
     if (njobs <= 0) return;
     {
@@ -45,11 +70,28 @@ public:
       ++gen_;
     }
     cv_.notify_all ();
+  }
+  bool help ()
+  {
+    if (!fn_) return false;
+    const int j = next_.fetch_add (1, std::memory_order_relaxed);
+    if (j >= njobs_) return false;
+    (*fn_) (j);
+    left_.fetch_sub (1, std::memory_order_release);
+    return true;
+  }
+  void end ()
+  {
+    if (!fn_) return;
     drain ();
-    // every job has been run and no worker is still inside this generation's loop (fn must outlive them)
     std::unique_lock<std::mutex> g (mu_);
     done_.wait (g, [this] { return left_.load (std::memory_order_acquire) == 0 && active_ == 0; });
     fn_ = nullptr; njobs_ = 0;
+  }
+  void run (int njobs, const std::function<void (int)>& fn)
+  {
+    if (njobs == 1) { fn (0); return; }                    // nothing to share: no wake-up
+    begin (njobs, fn); end ();
   }
 
 private:

@@ -14,6 +14,7 @@
 // dependency on it; without it the two entry points return B200TSDF_ESTATE and everything else works.
 #pragma once
 #include <dlfcn.h>
+#include <chrono>
 #include <nccl.h>
 
 namespace {
@@ -150,7 +151,6 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   if (!h->has_volume) return h->fail (B200TSDF_ESTATE, "integrateCloud before reset()");
   if (int rc = check_cloud_layout (h, stride, xyz_off, rgba_off, width, height)) return rc;
   constexpr int HALF = FRAME_RING / 2;
-  const int ROWS_CHUNK = h->rows_chunk;
   if (n > HALF) return h->fail (B200TSDF_EINVAL, "at most 32 frames per batch");
   if (n == 0) return B200TSDF_OK;
   cudaSetDevice (h->device);
@@ -162,7 +162,14 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   const size_t slice16 = (size_t) per * width * 16, frame16 = slice16 * nr;
   // host packing (host_pack.h): the caller's rows are packed to 16-byte pixels by host threads into pinned staging and only
   // those cross PCIe; without it the points are uploaded as they are (and packed on the device when there is a gather)
-  const bool hpack = h->host_pack && stride > 16;
+  // The host packs at ~115 GB/s machine-wide whatever the number of ranks (measured, tools/microbench/pack_bench.cu), a PCIe link
+  // uploads raw points at ~48 GB/s PER RANK: packing on the host wins for one or two ranks and loses from four on, where
+  // the raw slices are packed on the device instead.  B200TSDF_HOST_PACK=0 / 1 forces the choice.
+  const bool hpack = host_pack_wanted (h, stride, nr);
+  // frames per pipeline stage: with host packing short stages keep the copy engine right behind the packing threads (measured end
+  // to end on one GPU: 8 -> 6.4 k, 4 -> 7.4 k, 2 -> 7.9 k, 1 -> 8.0 k frames/s); a stage costs one NCCL launch when there is a
+  // gather, and device-side packing amortises its launches over 8
+  const int ROWS_CHUNK = h->rows_chunk > 0 ? h->rows_chunk : (hpack ? (nr == 1 ? 1 : 2) : 8);
   // two buffer sets, used alternately: set s is rewritten only after the batch that read it two calls ago has been fused
   const int s = h->rows_set;
   const size_t need_raw = hpack ? 0 : (size_t) HALF * per * width * stride, need_full = (size_t) HALF * frame16, need_pack = hpack ? (size_t) HALF * slice16 : 0;
@@ -181,49 +188,74 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
     }
     h->rows_raw_cap = need_raw; h->rows_full_cap = need_full; h->pack_cap = need_pack;
   }
-  if (hpack && !h->pack_pool)
-  {
-    int t = h->pack_threads;
-    if (t <= 0) { const int hw = (int) std::thread::hardware_concurrency (); t = std::max (1, std::min (16, hw / (2 * nr))); }
-    h->pack_pool = new b2host::PackPool (t);
-  }
-  // three-stage pipeline, ROWS_CHUNK frames per stage: the copy stream only uploads (the copy engine never waits for a
-  // kernel), the gather stream packs and all-gathers, the compute stream fuses.  Grid shapes without replayable launches
-  // are fused frame by frame once their chunk has arrived.
+  if (hpack) ensure_pack_pool (h, nr);
+  // three-stage pipeline over chunks of frames: the copy stream only uploads (the copy engine never waits for a kernel), the
+  // gather stream packs and all-gathers, the compute stream fuses.  Chunks are ROWS_CHUNK frames, the last one is halved down
+  // to 2 so that little is left to upload and fuse once the last pixel has been packed.  Grid shapes without replayable
+  // launches are fused frame by frame once their chunk has arrived.
   cudaStream_t cs = h->copy_stream, gs = h->gather_stream;
   if (int rc = pending_device_err (h)) return rc;
   if (h->rows_used[s]) { CK (cudaStreamWaitEvent (cs, h->ev_rows_done[s], 0)); CK (cudaStreamWaitEvent (gs, h->ev_rows_done[s], 0)); }
   const int npts = (row1 - row0) * width;
   const int out_rgba = (h->p.color && rgba_off >= 0) ? 12 : -1;
-  for (int c0 = 0; c0 < n; c0 += ROWS_CHUNK)
+  for (int i = 0; i < n; ++i) if (!rows[i] && slice_raw) return h->fail (B200TSDF_EINVAL, "null row slice in batch");
+  int cbeg[HALF + 1], nchunks = 0;
   {
-    const int m = std::min (ROWS_CHUNK, n - c0);
+    int at = 0;
+    while (n - at > ROWS_CHUNK) { cbeg[nchunks++] = at; at += ROWS_CHUNK; }
+    while (at < n) { const int rem = n - at, t = rem > 2 ? (rem + 1) / 2 : rem; cbeg[nchunks++] = at; at += t; }
+    cbeg[nchunks] = n;
+  }
+  static const bool trace = std::getenv ("B200TSDF_TRACE_ROWS") != nullptr;
+  double t_wait = 0, t_pack = 0, t_enq = 0;
+  auto now = [] { return std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now ().time_since_epoch ()).count (); };
+
+  // host packing: every job packs one block of rows of one frame, jobs in frame order; the pool works through the whole batch
+  // while this thread hands each chunk to the GPU as soon as its last block is packed (and packs along while it waits)
+  std::atomic<int> chunk_left[HALF];
+  int nb = 1;
+  unsigned char* const stage = hpack ? h->h_pack[s] : nullptr;
+  const int pack_rgba = h->p.color ? rgba_off : -1;
+  std::function<void (int)> job = [&] (int j)
+  {
+    const int i = j / nb, b = j % nb;
+    const size_t p0 = (size_t) npts * b / nb, p1 = (size_t) npts * (b + 1) / nb;
+    b2host::pack_points16 (static_cast<const unsigned char*> (rows[i]) + p0 * stride, stride, xyz_off, pack_rgba, p1 - p0, stage + (size_t) i * slice16 + p0 * 16);
+    int c = 0; while (cbeg[c + 1] <= i) ++c;
+    chunk_left[c].fetch_sub (1, std::memory_order_release);
+  };
+  struct PoolGuard { b2host::PackPool* p; ~PoolGuard () { if (p) p->end (); } } guard { nullptr };     // `job` must outlive the workers on every return path
+  if (hpack && npts)
+  {
+    // the staging is rewritten only after the uploads that read it two calls ago have left it
+    double t0 = trace ? now () : 0;
+    if (h->rows_used[s]) CK (cudaEventSynchronize (h->ev_rows_up[s][h->rows_last_up[s]]));
+    if (trace) t_wait += now () - t0;
+    nb = std::max (1, std::min ((4 * h->pack_pool->threads () + ROWS_CHUNK - 1) / ROWS_CHUNK, npts / 4096));
+    for (int c = 0; c < nchunks; ++c) chunk_left[c].store ((cbeg[c + 1] - cbeg[c]) * nb, std::memory_order_relaxed);
+    guard.p = h->pack_pool;
+    h->pack_pool->begin (n * nb, job);
+  }
+  for (int c = 0; c < nchunks; ++c)
+  {
+    const int c0 = cbeg[c], m = cbeg[c + 1] - c0;
     const bool raw_in_place = nr == 1 && !hpack;           // one rank, no host packing: fused where the points landed
     const void* ptrs[HALF];
     for (int i = 0; i < m; ++i)
       ptrs[i] = raw_in_place ? (const void*) (h->d_rows_raw[s] + (size_t) (c0 + i) * per * width * stride)
                              : (const void*) (h->d_rows_full[s] + (size_t) (c0 + i) * frame16);
     const size_t f_stride = raw_in_place ? stride : 16; const int f_xyz = raw_in_place ? xyz_off : 0, f_rgba = raw_in_place ? rgba_off : out_rgba;
-    for (int i = c0; i < c0 + m; ++i) if (!rows[i] && slice_raw) return h->fail (B200TSDF_EINVAL, "null row slice in batch");
+    double t0 = trace ? now () : 0;
+    if (hpack && npts)
+      while (chunk_left[c].load (std::memory_order_acquire) > 0)
+        if (!h->pack_pool->help ()) std::this_thread::yield ();
+    if (trace) { const double t = now (); t_pack += t - t0; t0 = t; }
     // the chunk's frame records travel on the copy stream ahead of its frames
     if (h->replayable) { if (int rc = batch_records (h, m, ptrs, f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) c0, cs)) return rc; }
     if (hpack)
     {
-      // the staging of this chunk is rewritten only after the upload that read it two calls ago has left it
-      if (h->rows_used[s]) CK (cudaEventSynchronize (h->ev_rows_up[s][c0 / ROWS_CHUNK]));
       if (npts)
       {
-        const int T = h->pack_pool->threads ();
-        const int nb = std::max (1, std::min ((4 * T + m - 1) / m, npts / 4096));         // row blocks per frame
-        unsigned char* stage = h->h_pack[s];
-        const int pack_rgba = h->p.color ? rgba_off : -1;
-        std::function<void (int)> job = [&] (int j)
-        {
-          const int i = c0 + j / nb, b = j % nb;
-          const size_t p0 = (size_t) npts * b / nb, p1 = (size_t) npts * (b + 1) / nb;
-          b2host::pack_points16 (static_cast<const unsigned char*> (rows[i]) + p0 * stride, stride, xyz_off, pack_rgba, p1 - p0, stage + (size_t) i * slice16 + p0 * 16);
-        };
-        h->pack_pool->run (m * nb, job);
         if (nr == 1) CK (cudaMemcpyAsync (h->d_rows_full[s] + (size_t) c0 * frame16, stage + (size_t) c0 * slice16, (size_t) m * slice16, cudaMemcpyHostToDevice, cs));
         else
           for (int i = c0; i < c0 + m; ++i)
@@ -237,8 +269,9 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
         if (slice_raw) CK (cudaMemcpyAsync (h->d_rows_raw[s] + (size_t) i * per * width * stride, rows[i], slice_raw, cudaMemcpyHostToDevice, cs));
         h->h2d_bytes += (long long) slice_raw;
       }
-    cudaEvent_t up = h->ev_rows_up[s][c0 / ROWS_CHUNK], ready = up;
+    cudaEvent_t up = h->ev_rows_up[s][c], ready = up;
     CK (cudaEventRecord (up, cs));
+    h->rows_last_up[s] = c;
     if (nr > 1)
     {
       CK (cudaStreamWaitEvent (gs, up, 0));
@@ -257,7 +290,7 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
       }
       NK (a.GroupEnd ());
       h->nvlink_bytes += (long long) m * (long long) slice16 * (nr - 1);
-      ready = h->ev_rows_ready[s][c0 / ROWS_CHUNK];
+      ready = h->ev_rows_ready[s][c];
       CK (cudaEventRecord (ready, gs));
     }
     CK (cudaStreamWaitEvent (h->stream, ready, 0));
@@ -265,8 +298,10 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
     else
       for (int i = 0; i < m; ++i)
         if (int rc = integrate_on_device (h, (const unsigned char*) ptrs[i], f_stride, f_xyz, f_rgba, width, height, poses_c2w + 16 * (size_t) (c0 + i))) return rc;
+    if (trace) t_enq += now () - t0;
   }
   CK (cudaEventRecord (h->ev_rows_done[s], h->stream));
+  if (trace) std::fprintf (stderr, "[b200tsdf rows] %d frames in %d chunks: staging wait %.2f ms, pack (this thread waiting / helping) %.2f ms, enqueue %.2f ms\n", n, nchunks, t_wait, t_pack, t_enq);
   h->rows_used[s] = true; h->rows_set ^= 1;
   return B200TSDF_OK;
 }
