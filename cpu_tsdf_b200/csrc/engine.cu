@@ -14,6 +14,9 @@
 #include "host_pack.h"
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -405,6 +408,50 @@ __global__ void k_mesh_roots (Params gp, McParams mc, unsigned long long* __rest
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
+// ---- pinned staging for the host-packed uploads ---------------------------------------------------------------
+// The packing threads read the caller's points and write the staging while the copy engine reads the staging: when all of it
+// sits behind ONE socket's memory controllers that socket is the bottleneck (measured, tools/microbench/pack_numa.cu: 32 frames
+// packed + uploaded in 3.6 ms with input and staging on the same node, 3.1 ms = the PCIe time with the staging elsewhere or
+// interleaved).  The staging is therefore interleaved over the NUMA nodes (mbind; best effort — a refusal leaves default
+// placement) and then pinned with cudaHostRegister.
+struct Staging
+{
+  unsigned char* p = nullptr; size_t bytes = 0;
+  int alloc (size_t n)
+  {
+    release ();
+    const size_t pg = 1ul << 21;                                     // (rounded to 2 MB: friendlier to transparent huge pages)
+    n = (n + pg - 1) / pg * pg;
+    void* m = mmap (nullptr, n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) return -1;
+    unsigned long mask = 0;
+    if (FILE* f = std::fopen ("/sys/devices/system/node/has_memory", "r"))
+    {
+      char line[256] = {};
+      if (std::fgets (line, sizeof (line), f))
+        for (const char* c = line; *c;)
+        {
+          char* e = nullptr; const long lo = std::strtol (c, &e, 10); if (e == c) break;
+          long hi = lo; if (*e == '-') { const char* b = e + 1; hi = std::strtol (b, &e, 10); if (e == b) break; }
+          for (long k = lo; k <= hi && k < 64; ++k) if (k >= 0) mask |= 1ul << k;
+          c = e; if (*c == ',') ++c; else break;
+        }
+      std::fclose (f);
+    }
+    if (mask & (mask - 1)) (void) syscall (SYS_mbind, m, n, 3 /* MPOL_INTERLEAVE */, &mask, (unsigned long) (8 * sizeof (mask)), 0u);
+    std::memset (m, 0, n);                                           // fault the pages in under that policy, before pinning
+    if (cudaHostRegister (m, n, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError (); munmap (m, n); return -1; }
+    p = static_cast<unsigned char*> (m); bytes = n;
+    return 0;
+  }
+  void release ()
+  {
+    if (!p) return;
+    cudaHostUnregister (p); munmap (p, bytes);
+    p = nullptr; bytes = 0;
+  }
+};
+
 struct b200tsdf
 {
   b200tsdf_config cfg_pending{}, cfg{};
@@ -462,8 +509,8 @@ struct b200tsdf
   int host_pack = -1;            // B200TSDF_HOST_PACK: 1 pack on the host, 0 upload the caller's points as they are (packed on the device when gathered); -1 by rank count
   int pack_threads = 0;          // B200TSDF_PACK_THREADS (0 = min (16, hardware threads / (2 ranks)))
   b2host::PackPool* pack_pool = nullptr;
-  unsigned char* h_pack[2] = { nullptr, nullptr }; size_t pack_cap = 0;
-  unsigned char* h_fpack[2] = { nullptr, nullptr };   // the same for the frame-at-a-time upload (d_frame[]), frame_cap bytes each
+  Staging h_pack[2]; size_t pack_cap = 0;
+  Staging h_fpack[2];            // the same for the frame-at-a-time upload (d_frame[]), frame_cap bytes each
   long long nvlink_bytes = 0, prof_nvlink0 = 0;
   int launches_per_frame = 0; long long graph_launches = 0, prof_graph0 = 0;
   // measurement
@@ -647,8 +694,7 @@ void b200tsdf_destroy (b200tsdf_t* h)
   for (int i = 0; i < 2; ++i)
   {
     cudaFree (h->d_rows_raw[i]); cudaFree (h->d_rows_full[i]);
-    if (h->h_pack[i]) cudaFreeHost (h->h_pack[i]);
-    if (h->h_fpack[i]) cudaFreeHost (h->h_fpack[i]);
+    h->h_pack[i].release (); h->h_fpack[i].release ();
     for (int k = 0; k < 32; ++k) { if (h->ev_rows_ready[i][k]) cudaEventDestroy (h->ev_rows_ready[i][k]); if (h->ev_rows_up[i][k]) cudaEventDestroy (h->ev_rows_up[i][k]); }
     if (h->ev_rows_done[i]) cudaEventDestroy (h->ev_rows_done[i]);
   }
@@ -1122,15 +1168,15 @@ static int integrate_host (b200tsdf* h, const void* points, size_t stride, int x
   const bool hpack = host_pack_wanted (h, stride, h->comm ? h->comm_size : 1);
   const size_t npts = (size_t) width * height;
   const size_t bytes = hpack ? npts * 16 : npts * stride;
-  if (bytes > h->frame_cap || (hpack && !h->h_fpack[0]))
+  if (bytes > h->frame_cap || (hpack && !h->h_fpack[0].p))
   {
     CK (cudaStreamSynchronize (h->stream)); CK (cudaStreamSynchronize (h->copy_stream));
     const size_t cap = std::max (bytes, h->frame_cap);
     for (int i = 0; i < 2; ++i)
     {
       cudaFree (h->d_frame[i]); h->d_frame[i] = nullptr; CK (cudaMalloc (&h->d_frame[i], cap));
-      if (h->h_fpack[i]) { cudaFreeHost (h->h_fpack[i]); h->h_fpack[i] = nullptr; }
-      if (hpack) CK (cudaHostAlloc (&h->h_fpack[i], cap, cudaHostAllocDefault));
+      h->h_fpack[i].release ();
+      if (hpack && h->h_fpack[i].alloc (cap)) return h->fail (B200TSDF_ENOMEM, "pinned staging for the packed upload");
     }
     h->frame_cap = cap;
     h->frame_no = 0;
@@ -1149,7 +1195,7 @@ static int integrate_host (b200tsdf* h, const void* points, size_t stride, int x
     ensure_pack_pool (h, h->comm ? h->comm_size : 1);
     const int nb = (int) std::max<size_t> (1, std::min<size_t> (4 * (size_t) h->pack_pool->threads (), npts / 4096));
     const int pack_rgba = h->p.color ? rgba_off : -1;
-    unsigned char* stage = h->h_fpack[b];
+    unsigned char* stage = h->h_fpack[b].p;
     std::function<void (int)> job = [&] (int j)
     {
       const size_t p0 = npts * (size_t) j / nb, p1 = npts * (size_t) (j + 1) / nb;

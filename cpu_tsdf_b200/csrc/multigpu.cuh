@@ -179,11 +179,11 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
     for (int k = 0; k < 2; ++k)
     {
       cudaFree (h->d_rows_raw[k]); cudaFree (h->d_rows_full[k]); h->d_rows_raw[k] = h->d_rows_full[k] = nullptr;
-      if (h->h_pack[k]) { cudaFreeHost (h->h_pack[k]); h->h_pack[k] = nullptr; }
+      h->h_pack[k].release ();
       h->rows_raw_cap = h->rows_full_cap = h->pack_cap = 0;
       if (need_raw) CK (cudaMalloc (&h->d_rows_raw[k], need_raw));
       CK (cudaMalloc (&h->d_rows_full[k], need_full));
-      if (need_pack) CK (cudaHostAlloc (&h->h_pack[k], need_pack, cudaHostAllocDefault));
+      if (need_pack && h->h_pack[k].alloc (need_pack)) return h->fail (B200TSDF_ENOMEM, "pinned staging for the packed upload");
       h->rows_used[k] = false;
     }
     h->rows_raw_cap = need_raw; h->rows_full_cap = need_full; h->pack_cap = need_pack;
@@ -214,7 +214,7 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   // while this thread hands each chunk to the GPU as soon as its last block is packed (and packs along while it waits)
   std::atomic<int> chunk_left[HALF];
   int nb = 1;
-  unsigned char* const stage = hpack ? h->h_pack[s] : nullptr;
+  unsigned char* const stage = hpack ? h->h_pack[s].p : nullptr;
   const int pack_rgba = h->p.color ? rgba_off : -1;
   std::function<void (int)> job = [&] (int j)
   {

@@ -36,3 +36,12 @@ def test_shim_example_runs(engine_lib):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mesh:" in r.stdout
+
+
+def test_host_packing_is_bit_preserving_and_the_pool_runs_every_job_once(tmp_path):
+    """cpu_tsdf_b200/csrc/host_pack.h (the host half of the batched upload): tests/cpp/pack_test.cpp checks the packed pixels
+    against the source bytes for the SSE and the generic paths, and the fork/join pool under run() and begin()/help()/end()."""
+    exe = str(tmp_path / "pack_test")
+    subprocess.run([CXX, "-std=c++17", "-O2", "-pthread", os.path.join(ROOT, "tests", "cpp", "pack_test.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr

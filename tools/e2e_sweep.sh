@@ -5,8 +5,7 @@ run () { env "$@" python bench.py --no-cpu-baseline --no-host-load 2>/dev/null |
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$*', round(d['value']), round(d['e2e']['value']))" >> $out; }
 for r in 1 2 3; do
-run B200TSDF_ROWS_CHUNK=1
-run B200TSDF_ROWS_CHUNK=2
-run B200TSDF_ROWS_CHUNK=2 B200TSDF_PACK_THREADS=12
+run A=default
+run B200TSDF_PACK_THREADS=24
 done
 sort $out
