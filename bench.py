@@ -58,7 +58,7 @@ class HostLoad:
     def __enter__(self):
         for _ in range(self.n):
             self.procs.append(subprocess.Popen([sys.executable, "-c", "while True: pass"]))
-        time.sleep(0.5)
+        time.sleep(2.0)                      # 128 interpreters booting at once are a fork storm, not the steady load that is meant
         return self
 
     def __exit__(self, *a):
@@ -350,21 +350,6 @@ def main():
         step_device_frames(k); k += FRAMES_PER_STEP
     prof_f, ms_frames = timed(step_device_frames, args.steps)
 
-    # ---- the batched leg again with every host core busy (a library must not depend on an idle host) ----
-    host_load = None
-    if not args.no_host_load:
-        import contextlib
-        with (HostLoad(os.cpu_count() or 1) if rank == 0 else contextlib.nullcontext()):
-            step_device(k); k += FRAMES_PER_STEP
-            vol.sync()
-            n_loaded = max(16, args.steps)
-            loaded = []
-            for _ in range(3):                                 # three repeats: a descheduled submitting thread shows as an outlier, not as the figure
-                _, ms_loaded = timed(step_device, n_loaded)
-                loaded.append(n_loaded * FRAMES_PER_STEP / (ms_loaded / 1e3))
-        host_load = {"value": sorted(loaded)[1], "unit": "frames/s", "steps": n_loaded, "repeats": loaded, "statistic": "median of 3 repeats",
-                     "load": f"{os.cpu_count()} busy-loop processes (one per host core) during the batched device-resident leg"}
-
     # ---- end-to-end leg (host buffers, public API) ---------------------------------------------
     host_pack = os.environ.get("B200TSDF_HOST_PACK", "1" if world <= 2 else "0") != "0"     # the library's own default (multigpu.cuh)
     pack_threads = int(os.environ.get("B200TSDF_PACK_THREADS", "0")) or max(1, min(16, (os.cpu_count() or 1) // (2 * world)))
@@ -383,6 +368,22 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = nframes / (float(e2e_ms.item()) / 1e3)
+
+    # ---- the batched leg again with every host core busy (a library must not depend on an idle host); last, so that
+    #      the 128 busy loops do not colour the end-to-end leg ----
+    host_load = None
+    if not args.no_host_load:
+        import contextlib
+        with (HostLoad(os.cpu_count() or 1) if rank == 0 else contextlib.nullcontext()):
+            step_device(k); k += FRAMES_PER_STEP
+            vol.sync()
+            n_loaded = max(16, args.steps)
+            loaded = []
+            for _ in range(3):                                 # three repeats: a descheduled submitting thread shows as an outlier, not as the figure
+                _, ms_loaded = timed(step_device, n_loaded)
+                loaded.append(n_loaded * FRAMES_PER_STEP / (ms_loaded / 1e3))
+        host_load = {"value": sorted(loaded)[1], "unit": "frames/s", "steps": n_loaded, "repeats": loaded, "statistic": "median of 3 repeats",
+                     "load": f"{os.cpu_count()} busy-loop processes (one per host core) during the batched device-resident leg"}
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     upd = torch.tensor([prof.n_updates], dtype=torch.float64, device="cuda")

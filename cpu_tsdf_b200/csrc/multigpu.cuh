@@ -225,12 +225,15 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
     chunk_left[c].fetch_sub (1, std::memory_order_release);
   };
   struct PoolGuard { b2host::PackPool* p; ~PoolGuard () { if (p) p->end (); } } guard { nullptr };     // `job` must outlive the workers on every return path
-  if (hpack && npts)
   {
-    // the staging is rewritten only after the uploads that read it two calls ago have left it
+    // the uploads of the call before last (same buffer set) have left the host: the packed staging may be rewritten, and the
+    // caller's rows of that call are free (the contract of the unpacked path: valid "until two further calls")
     double t0 = trace ? now () : 0;
     if (h->rows_used[s]) CK (cudaEventSynchronize (h->ev_rows_up[s][h->rows_last_up[s]]));
     if (trace) t_wait += now () - t0;
+  }
+  if (hpack && npts)
+  {
     nb = std::max (1, std::min ((4 * h->pack_pool->threads () + ROWS_CHUNK - 1) / ROWS_CHUNK, npts / 4096));
     for (int c = 0; c < nchunks; ++c) chunk_left[c].store ((cbeg[c + 1] - cbeg[c]) * nb, std::memory_order_relaxed);
     guard.p = h->pack_pool;

@@ -80,7 +80,10 @@ int  b200tsdf_reset (b200tsdf_t* h);
  * row-major (cloud(u,v) = points[v*W+u]), `stride` bytes per point, xyz as 3 floats at
  * xyz_off, PCL colour bytes (b,g,r,a) at rgba_off or -1.  NaN z = invalid.  pose_c2w =
  * camera->world Affine3d as a row-major 4x4.  The normals argument of the reference is unused
- * there (hpp:51) and has no counterpart.  The host buffer is not retained after return. */
+ * there (hpp:51) and has no counterpart.  The host buffer is not retained after return.
+ * Points wider than 16 bytes are packed to 16-byte pixels {x, y, z, bgra} on the host (a small pool of worker threads,
+ * csrc/host_pack.h; bit-preserving) so that only the bytes the fusion reads cross PCIe — pageable clouds included; environment
+ * switches in INTEGRATION.md §5. */
 int  b200tsdf_integrate (b200tsdf_t* h, const void* points, size_t stride, int xyz_off, int rgba_off,
                          int width, int height, const double* pose_c2w);
 /* same, with the cloud already resident in device memory of h's device (no copy, async on the
@@ -97,7 +100,8 @@ int  b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d
 /* streaming variant of b200tsdf_integrate for producers that keep their (pinned) frame buffers alive:
  * returns as soon as the copy and the kernels are enqueued.  `points` must stay valid and unmodified
  * until b200tsdf_sync() or until two further frames have been submitted on this handle (the call that submits
- * frame i+2 waits for the upload of frame i before it returns).
+ * frame i+2 waits for the upload of frame i before it returns); when the upload is packed on the host (see
+ * b200tsdf_integrate) the buffer is already free on return.
  * Error reporting of the asynchronous entry points (integrate_device / _batch_device / _async, and integrate itself, which
  * waits for its upload only): a device-side failure of frame i (brick pool exhausted, work queue overflow) is reported by
  * the next call on the handle (integrate*, query, render) and at the latest by sync / get_stats / mesh / save. */
@@ -207,7 +211,8 @@ int  b200tsdf_row_slice (const b200tsdf_t* h, int height, int* row0, int* row1);
  * (rows[i] -> points (v * width + u), v in the slice; layout as for b200tsdf_integrate).  The slice is uploaded over this
  * GPU's PCIe link, packed to 16-byte pixels and all-gathered over NVLink into the full frame on every rank (collective: all
  * ranks call with the same n), then the batch is fused like b200tsdf_integrate_batch_device.  Without a communicator the
- * slice is the whole frame and nothing is exchanged.  rows[i] must stay valid until b200tsdf_sync or two further calls. */
+ * slice is the whole frame and nothing is exchanged.  With one or two ranks the slice is packed on the host first (see
+ * b200tsdf_integrate) and rows[i] are free on return; otherwise they must stay valid until b200tsdf_sync or two further calls. */
 int  b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows, size_t stride, int xyz_off, int rgba_off,
                                     int width, int height, const double* poses_c2w);
 /* Collective: every rank's shard goes device to device (NCCL send/recv over NVLink, no host staging) to rank `root`, which
