@@ -1150,7 +1150,9 @@ static void ensure_pack_pool (b200tsdf* h, int nr)
       }
     }
   }
-  h->pack_pool = new b2host::PackPool (t, cpus);
+  // (no exception may cross the C ABI: if the threads cannot be created the caller's thread packs alone)
+  try { h->pack_pool = new b2host::PackPool (t, cpus); }
+  catch (...) { h->pack_pool = new b2host::PackPool (1); }
 }
 
 // is the upload of `stride`-byte points packed on the host?  (-1: by rank count, see b200tsdf_integrate_batch_rows)
@@ -1954,6 +1956,8 @@ int b200tsdf_load (b200tsdf_t* h, const char* path)
                            &c.min_sensor_dist, &c.max_sensor_dist, &c.max_cell_x, &c.max_cell_y, &c.max_cell_z,
                            &c.fx, &c.fy, &c.cx, &c.cy, &c.image_width, &c.image_height, &is_empty, &wd, &wv);
   if (nread != 23) return fail ("bad header");
+  // the reference has no setter for these two: only a .vol written with them set turns the alternative weightings on (hpp:200-204)
+  if (wd || wv) return fail ("weight_by_depth_ / weight_by_variance_ volumes are not supported (the fusion here uses w_new = 1)");
   char pct[8]; int rr = 0, cc = 0;
   if (std::fscanf (f, " %1s %d %d", pct, &rr, &cc) != 3 || pct[0] != '%' || rr != 4 || cc != 4) return fail ("bad transform header");
   for (int i = 0; i < 16; ++i) if (std::fscanf (f, "%lf", &gt[i]) != 1) return fail ("bad transform");

@@ -45,7 +45,8 @@ public:
     }
     for (int i = 0; i < threads - 1; ++i)
     {
-      th_.emplace_back ([this] { worker (); });                                         // the caller is the last worker
+      try { th_.emplace_back ([this] { worker (); }); }                                 // the caller is the last worker
+      catch (...) { break; }                                                            // (thread limit reached: a smaller pool)
       if (confine) pthread_setaffinity_np (th_.back ().native_handle (), sizeof (set), &set);
     }
   }

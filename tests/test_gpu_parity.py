@@ -271,6 +271,16 @@ def test_load_vol_written_by_the_reference_path(tmp_path):
     assert open(pa, "rb").read() == open(pb, "rb").read()
     with pytest.raises(pkg.B200Error):
         v.load(str(tmp_path / "missing.vol"))
+    # a header that switches weight_by_depth_ on (cpp:240, 265; hpp:200-201) is refused, not silently fused with w_new = 1
+    raw = open(pa, "rb").read()
+    head, tail = raw.split(b"% 4 4", 1)
+    lines = head.split(b"\n")
+    assert lines[-3:-1] == [b"0", b"0"]                       # weight_by_depth_, weight_by_variance_ (the last header lines before the transform)
+    lines[-3] = b"1"
+    pc = str(tmp_path / "c.vol")
+    open(pc, "wb").write(b"\n".join(lines) + b"% 4 4" + tail)
+    with pytest.raises(pkg.B200Error, match="weight_by"):
+        v.load(pc)
 
 
 def _engine_2048(general=False, pool_log2=18):
