@@ -351,7 +351,7 @@ def main():
     prof_f, ms_frames = timed(step_device_frames, args.steps)
 
     # ---- end-to-end leg (host buffers, public API) ---------------------------------------------
-    host_pack = os.environ.get("B200TSDF_HOST_PACK", "1" if world <= 2 else "0") != "0"     # the library's own default (multigpu.cuh)
+    host_pack = os.environ.get("B200TSDF_HOST_PACK", "1" if world <= 1 else "0") != "0"     # the library's own default (multigpu.cuh)
     pack_threads = int(os.environ.get("B200TSDF_PACK_THREADS", "0")) or max(1, min(16, (os.cpu_count() or 1) // (2 * world)))
     for _ in range(max(1, args.warmup // 2)):
         step_host(k); k += FRAMES_PER_STEP

@@ -1156,7 +1156,7 @@ static void ensure_pack_pool (b200tsdf* h, int nr)
 }
 
 // is the upload of `stride`-byte points packed on the host?  (-1: by rank count, see b200tsdf_integrate_batch_rows)
-static bool host_pack_wanted (const b200tsdf* h, size_t stride, int nr) { return (h->host_pack < 0 ? nr <= 2 : h->host_pack != 0) && stride > 16; }
+static bool host_pack_wanted (const b200tsdf* h, size_t stride, int nr) { return (h->host_pack < 0 ? nr <= 1 : h->host_pack != 0) && stride > 16; }
 
 static int integrate_host (b200tsdf* h, const void* points, size_t stride, int xyz_off, int rgba_off,
                            int width, int height, const double* pose, bool wait_copy)

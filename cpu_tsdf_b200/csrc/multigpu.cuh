@@ -163,8 +163,9 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   // host packing (host_pack.h): the caller's rows are packed to 16-byte pixels by host threads into pinned staging and only
   // those cross PCIe; without it the points are uploaded as they are (and packed on the device when there is a gather)
   // The host packs at ~115 GB/s machine-wide whatever the number of ranks (measured, tools/microbench/pack_bench.cu), a PCIe link
-  // uploads raw points at ~48 GB/s PER RANK: packing on the host wins for one or two ranks and loses from four on, where
-  // the raw slices are packed on the device instead.  B200TSDF_HOST_PACK=0 / 1 forces the choice.
+  // uploads raw points at ~48 GB/s PER RANK: packing on the host wins for one rank (8.0 k against 4.9 k frames/s), is a draw
+  // at two (6.4-7.7 k packed, 7.6 k raw) and loses from four on; with more than one rank the raw slices are therefore
+  // packed on the device.  B200TSDF_HOST_PACK=0 / 1 forces the choice.
   const bool hpack = host_pack_wanted (h, stride, nr);
   // frames per pipeline stage: with host packing short stages keep the copy engine right behind the packing threads (measured end
   // to end on one GPU: 8 -> 6.4 k, 4 -> 7.4 k, 2 -> 7.9 k, 1 -> 8.0 k frames/s); a stage costs one NCCL launch when there is a

@@ -211,7 +211,7 @@ int  b200tsdf_row_slice (const b200tsdf_t* h, int height, int* row0, int* row1);
  * (rows[i] -> points (v * width + u), v in the slice; layout as for b200tsdf_integrate).  The slice is uploaded over this
  * GPU's PCIe link, packed to 16-byte pixels and all-gathered over NVLink into the full frame on every rank (collective: all
  * ranks call with the same n), then the batch is fused like b200tsdf_integrate_batch_device.  Without a communicator the
- * slice is the whole frame and nothing is exchanged.  With one or two ranks the slice is packed on the host first (see
+ * slice is the whole frame and nothing is exchanged.  With a single rank the slice is packed on the host first (see
  * b200tsdf_integrate) and rows[i] are free on return; otherwise they must stay valid until b200tsdf_sync or two further calls. */
 int  b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows, size_t stride, int xyz_off, int rgba_off,
                                     int width, int height, const double* poses_c2w);
