@@ -10,15 +10,28 @@ ia, isrc, ismp = h.index("Instructions Executed"), h.index("Source"), h.index("#
 ins = [r for r in rows[2:] if len(r) > ia and r[0] not in ("Address", "Kernel Name")]
 cnt = [int(r[ia]) for r in ins]; smp = [int(r[ismp]) for r in ins]
 tot, stot = sum(cnt), sum(smp)
-thr = 0.6 * max(cnt)
-hot = [i for i, c in enumerate(cnt) if c >= thr]
-lo, hi = min(hot), max(hot)
+# the finest-voxel loop = the innermost backward branch whose body stores a {sdf, weight} pair of the finest level (node 72 + ...: +0x240)
+import re
+addr = {}
+for i, r in enumerate(ins):
+    try: addr[int(r[0], 16)] = i
+    except ValueError: pass
+lo = hi = None
+for i, r in enumerate(ins):
+    m = re.search(r"BRA(?:\.\w+)*\s+(?:!?U?P\w+,\s*)?0x([0-9a-f]+)", r[isrc])
+    if not m: continue
+    j = addr.get(int(m.group(1), 16))
+    if j is None or j >= i: continue
+    body = " ".join(x[isrc] for x in ins[j:i + 1])
+    if "STG.E.64" in body and "+0x240]" in body and (lo is None or i - j < hi - lo): lo, hi = j, i
 loop_exec = sum(cnt[lo:hi + 1])
-rounds = cnt[lo]
+iters = cnt[lo]
+unroll = 2 if (hi - lo) > 450 else 1
+rounds = iters * unroll
 print(f"{kname[:80]}")
 print(f"ncu --set full --import-source on, one launch (frame 20 of tools/prof_integrate.py, 2048^3 / 10 m, colour): {tot} warp instructions, {len(ins)} static SASS instructions, {stot} stall samples")
-print(f"finest-voxel loop = SASS instructions {lo}..{hi} ({hi - lo + 1} static, incl. the rarely taken double-precision projection): {loop_exec} executed = {100.0 * loop_exec / tot:.1f} % of the kernel,")
-print(f"  ~{loop_exec / rounds:.0f} per round of 32 voxels ({rounds} rounds), {sum(smp[lo:hi + 1])} of the stall samples")
+print(f"finest-voxel loop = SASS instructions {lo}..{hi} ({hi - lo + 1} static for {unroll} round(s), incl. the rarely taken double-precision projection): {loop_exec} executed = {100.0 * loop_exec / tot:.1f} % of the kernel,")
+print(f"  ~{loop_exec / rounds:.0f} per round of 32 voxels (~{rounds} rounds), {sum(smp[lo:hi + 1])} of the stall samples")
 op = collections.Counter()
 for i in range(lo, hi + 1):
     s = ins[i][isrc].split()
