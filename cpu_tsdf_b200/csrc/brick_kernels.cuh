@@ -74,14 +74,14 @@ __device__ __forceinline__ NodePos qnode_pos (const Params& p, int level, const 
 
 // Appends the 8 children of `n` to the next level's queue.  Called by every lane of the warp with
 // `want` saying whether this lane pushes: one atomicAdd per warp reserves the whole range.
-__device__ __forceinline__ bool push_children (const Params& p, const Queues& Q, int li, bool want, const NodePos& n, int cs, QNode& e)
+__device__ __forceinline__ bool push_children (const Params& p, const Queues& Q, int* qn, int li, bool want, const NodePos& n, int cs, QNode& e)
 {
   const unsigned lane = threadIdx.x & 31;
   const unsigned mask = __ballot_sync (0xffffffffu, want);
   if (!mask) return false;
   int base = 0;
   const int leader = __ffs (mask) - 1;
-  if ((int) lane == leader) base = atomicAdd (&Q.n[li + 1], 8 * __popc (mask));
+  if ((int) lane == leader) base = atomicAdd (&qn[li + 1], 8 * __popc (mask));
   base = __shfl_sync (0xffffffffu, base, leader);
   if (!want) return false;
   base += 8 * __popc (mask & ((1u << lane) - 1));
@@ -114,11 +114,26 @@ __device__ __forceinline__ void warp_add_stats (unsigned long long* stats, unsig
 // ---- 1. top-down over the upper levels: one thread per queued node ---------------------------------
 // `block_level`: the queue holds block roots (level L-3); interior ones go to the block list with their
 // brick slot instead of having their children queued.
-__global__ void k_upper_down (Params p, Frame f, Queues Q, int li, int block_level, int* __restrict__ blist, int* __restrict__ bcount,
+// The frame comes from its record in device memory and the counters from the record's counter set (Q.n = the base of all
+// sets), so that the launch can be captured into a graph and replayed like the other kernels of a frame.
+#define B2_UPPER_FRAME(fr)                                                                   \
+  __shared__ Frame s_uf_;                                                                    \
+  {                                                                                          \
+    const int* src_ = reinterpret_cast<const int*> (&(fr)->f);                               \
+    int* dst_ = reinterpret_cast<int*> (&s_uf_);                                             \
+    for (int w_ = threadIdx.x; w_ < (int) (sizeof (Frame) / sizeof (int)); w_ += blockDim.x) dst_[w_] = src_[w_]; \
+  }                                                                                          \
+  __syncthreads ();                                                                          \
+  const Frame& f = s_uf_;                                                                    \
+  int* const qn = Q.n + 16 * (fr)->cset;
+
+__global__ void k_upper_down (Params p, const FrameRec* __restrict__ fr, Queues Q, int li, int block_level, int* __restrict__ blist,
                               unsigned long long* __restrict__ stats)
 {
+  B2_UPPER_FRAME (fr)
+  int* const bcount = qn + 9;
   int level = p.C + li;
-  int count = Q.n[li];
+  int count = qn[li];
   if (count > Q.cap[li]) count = Q.cap[li];
   unsigned long long upd = 0, vis = 0;
   const int stride = gridDim.x * blockDim.x;
@@ -165,7 +180,7 @@ __global__ void k_upper_down (Params p, Frame f, Queues Q, int li, int block_lev
         }
       }
     }
-    if (!block_level) push_children (p, Q, li, push, n, cs, e);
+    if (!block_level) push_children (p, Q, qn, li, push, n, cs, e);
     else
     {
       // interior block roots go to the block list (one atomic per warp)
@@ -186,10 +201,11 @@ __global__ void k_upper_down (Params p, Frame f, Queues Q, int li, int block_lev
 }
 
 // ---- 3. bottom-up over the upper levels -------------------------------------------------------------
-__global__ void k_upper_up (Params p, Frame f, Queues Q, int li, unsigned long long* __restrict__ stats)
+__global__ void k_upper_up (Params p, const FrameRec* __restrict__ fr, Queues Q, int li, unsigned long long* __restrict__ stats)
 {
+  B2_UPPER_FRAME (fr)
   int level = p.C + li;
-  int count = Q.n[li];
+  int count = qn[li];
   if (count > Q.cap[li]) count = Q.cap[li];
   unsigned long long upd = 0, vis = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)

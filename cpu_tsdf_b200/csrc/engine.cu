@@ -825,7 +825,7 @@ int b200tsdf_reset (b200tsdf_t* h)
       }
       if (h->super_static && !h->d_superq) CK (cudaMalloc (&h->d_superq, 4096 * sizeof (QNode)));
     }
-    h->replayable = h->top_path && h->nup == 0;           // (k_upper_* still take the frame by value)
+    h->replayable = h->fast_path;                         // every kernel of the brick paths reads the frame from its record (the general depth-first kernel takes it by value)
     size_t bl = h->q_levels ? caps[h->q_levels - 1] : 0;
     if (h->top_path) bl = std::max (bl, (size_t) h->cell_cap * 512);
     if (bl > h->blist_cap)
@@ -902,7 +902,6 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
   const Params& p = h->p;
   const Frame& f = rec.f;
   int* cnt = h->d_count + 16 * rec.cset;
-  h->Q.n = cnt;
   const int npix = f.width * f.height;
   const int ncells = 1 << (3 * p.C);
   {
@@ -921,12 +920,11 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
   if (h->fast_path)
   {
     const int nl = h->q_levels;
-    int* d_bcount = cnt + 9;
     QNode* bq = nullptr;                                   // the queue the block-root entries of k_bricks live in
     if (h->top_path)
     {
       // coarse levels above the supercells, top-down (none for 2048^3 / 10 m and 512^3 / 3 m)
-      for (int li = 0; li < h->nup; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, 0, h->d_blist, d_bcount, h->d_stats); h->launches++; }
+      for (int li = 0; li < h->nup; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, d_rec, h->Q, li, 0, h->d_blist, h->d_stats); h->launches++; }
       QNode* cells = h->super_static ? h->d_superq : h->Q.q[h->nup];
       const int qslot = h->super_static ? -1 : h->nup;
       auto kd = p.color ? k_celltop_down<true> : k_celltop_down<false>;
@@ -937,7 +935,7 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
     }
     else
     {
-      for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, li == nl - 1, h->d_blist, d_bcount, h->d_stats); h->launches++; }
+      for (int li = 0; li < nl; ++li) { k_upper_down<<<148 * 2, 128, 0, s>>> (p, d_rec, h->Q, li, li == nl - 1, h->d_blist, h->d_stats); h->launches++; }
       bq = h->Q.q[nl - 1];
     }
     if (kr >= 0) CK (cudaEventRecord (h->kring[kr][0], s));
@@ -958,10 +956,10 @@ static int launch_frame (b200tsdf* h, cudaStream_t s, const FrameRec& rec, const
       if (h->use_pdl) CK (launch_pdl (ku, dim3 (h->sm_count), dim3 (128), s, p, d_rec, cells, (const int*) h->d_count, (const QNode*) h->d_cellq, (const CellTop*) h->d_celltop, h->cell_cap, h->d_stats, h->sl, qslot, h->super_static));
       else ku<<<h->sm_count, 128, 0, s>>> (p, d_rec, cells, h->d_count, h->d_cellq, h->d_celltop, h->cell_cap, h->d_stats, h->sl, qslot, h->super_static);
       h->launches++;
-      for (int li = h->nup - 1; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
+      for (int li = h->nup - 1; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, d_rec, h->Q, li, h->d_stats); h->launches++; }
     }
     else
-      for (int li = nl - 2; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, f, h->Q, li, h->d_stats); h->launches++; }
+      for (int li = nl - 2; li >= 0; --li) { k_upper_up<<<148 * 2, 128, 0, s>>> (p, d_rec, h->Q, li, h->d_stats); h->launches++; }
   }
   else
   {
@@ -1109,7 +1107,7 @@ int b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_
     const int m = std::min (HALF, n - done);
     if (!h->replayable)
     {
-      // grid shapes whose launches are not replayable: frame by frame
+      // the general depth-first kernel takes the frame by value: frame by frame
       for (int i = 0; i < m; ++i)
         if (int rc = integrate_on_device (h, (const unsigned char*) d_points[done + i], stride, xyz_off, rgba_off, width, height, poses_c2w + 16 * (size_t) (done + i))) return rc;
       done += m;

@@ -192,7 +192,7 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   if (hpack) ensure_pack_pool (h, nr);
   // three-stage pipeline over chunks of frames: the copy stream only uploads (the copy engine never waits for a kernel), the
   // gather stream packs and all-gathers, the compute stream fuses.  Chunks are ROWS_CHUNK frames, the last one is halved down
-  // to 2 so that little is left to upload and fuse once the last pixel has been packed.  Grid shapes without replayable
+  // to 2 so that little is left to upload and fuse once the last pixel has been packed.  Configurations without replayable
   // launches are fused frame by frame once their chunk has arrived.
   cudaStream_t cs = h->copy_stream, gs = h->gather_stream;
   if (int rc = pending_device_err (h)) return rc;

@@ -94,7 +94,8 @@ int  b200tsdf_integrate_device (b200tsdf_t* h, const void* d_points, size_t stri
  * parameters go to the device in one copy and the launches of the whole batch are one CUDA-graph launch (captured once
  * per batch size, replayed afterwards), so the host issues ~3 driver calls per batch instead of ~6 per frame.
  * d_points: n device pointers (same layout for all); poses_c2w: n row-major 4x4 matrices back to back.  Asynchronous
- * like b200tsdf_integrate_device.  Grid shapes without a replayable launch sequence are fused frame by frame. */
+ * like b200tsdf_integrate_device.  Configurations fused by the general depth-first kernel (track_variance, RGBNormalized payload)
+ * are fused frame by frame inside the same call. */
 int  b200tsdf_integrate_batch_device (b200tsdf_t* h, int n, const void* const* d_points, size_t stride, int xyz_off, int rgba_off,
                                       int width, int height, const double* poses_c2w);
 /* streaming variant of b200tsdf_integrate for producers that keep their (pinned) frame buffers alive:

@@ -338,6 +338,27 @@ def test_4096_three_tiers_config5_shape():
     assert_same_nodes(o.dump_nodes(), e.download_nodes())
 
 
+def test_4096_batches_replay_graphs_with_the_coarse_sweeps():
+    """Shapes with coarse levels above the tier-1 supercells (4096^3 / 10 m: one such level) launch k_upper_down / k_upper_up
+    around the four fused kernels; these read the frame from its record too, so a batch is one captured graph.  Two batches
+    (3 + 3 frames: capture, then replay on the other half of the record ring) against the oracle frame by frame."""
+    import torch
+    cfg = dict(xres=4096, yres=4096, zres=4096, xsize=10.0, ysize=10.0, zsize=10.0, cx=CAM.cx, cy=CAM.cy)
+    o, e = pair(cfg, 19)
+    fs = list(frames(synth.S2, 6, stride=3, noise_seed=8))
+    dev = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for _, c in fs]
+    for pose, cloud in fs:
+        o.integrate(cloud, pose)
+    H, W = fs[0][1].shape[:2]
+    e.profile_begin()
+    for lo, hi in ((0, 3), (3, 6)):
+        e.integrateBatchDevice([d.data_ptr() for d in dev[lo:hi]], H, W, 4 * fs[0][1].shape[2], [p for p, _ in fs[lo:hi]])
+    prof = e.profile_end()
+    assert prof.graph_launches == 2
+    assert_same_nodes(o.dump_nodes(), e.download_nodes())
+    assert e.stats().n_updates == o.stats().n_add_observation
+
+
 def test_shards_gathered_into_one_volume_render_like_the_whole():
     # multi-GPU read side (SURVEY.md §8e): integrate in shards, gather the shards into one volume, render / mesh there
     o = OracleVolume(**CFG_512); o.reset()
@@ -382,8 +403,8 @@ def test_batch_graph_replay_matches_the_oracle_and_frame_by_frame():
     e.sync()
     assert_same_nodes(o.dump_nodes(), e.download_nodes(), rgb=True)
     assert e.stats().n_updates == o.stats().n_add_observation
-    # a grid shape without a replayable launch sequence takes the frame-by-frame route inside the same call
-    o2, e2 = pair(CFG_256, 16)
+    # a configuration fused by the general depth-first kernel (here: track_variance) takes the frame-by-frame route inside the same call
+    o2, e2 = pair(CFG_256, 16, track_variance=1)
     fs2 = list(frames(synth.S1, 3, stride=9, noise_seed=5))
     dev2 = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for _, c in fs2]
     for pose, cloud in fs2:
