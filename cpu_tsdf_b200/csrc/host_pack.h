@@ -135,6 +135,19 @@ private:
   bool stop_ = false;
 };
 
+// Pipeline stages of a batch of n frames: stages of `chunk` frames while more than `chunk` remain, then the remainder halved down to
+// 2 frames, so that little is left to upload and fuse once the last frame has been packed / uploaded.  cbeg[0 .. return] are the
+// stage boundaries (cbeg[0] = 0, cbeg[return] = n); at most n stages.
+inline int stage_schedule (int n, int chunk, int* cbeg)
+{
+  int k = 0, at = 0;
+  if (chunk < 1) chunk = 1;
+  while (n - at > chunk) { cbeg[k++] = at; at += chunk; }
+  while (at < n) { const int rem = n - at, t = rem > 2 ? (rem + 1) / 2 : rem; cbeg[k++] = at; at += t; }
+  cbeg[k] = n;
+  return k;
+}
+
 // n points of `stride` bytes -> n 16-byte pixels {x, y, z, colour word}; rgba_off < 0: colour word 0
 inline void pack_points16 (const unsigned char* in, size_t stride, int xyz_off, int rgba_off, size_t n, unsigned char* out)
 {

@@ -200,13 +200,8 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
   const int npts = (row1 - row0) * width;
   const int out_rgba = (h->p.color && rgba_off >= 0) ? 12 : -1;
   for (int i = 0; i < n; ++i) if (!rows[i] && slice_raw) return h->fail (B200TSDF_EINVAL, "null row slice in batch");
-  int cbeg[HALF + 1], nchunks = 0;
-  {
-    int at = 0;
-    while (n - at > ROWS_CHUNK) { cbeg[nchunks++] = at; at += ROWS_CHUNK; }
-    while (at < n) { const int rem = n - at, t = rem > 2 ? (rem + 1) / 2 : rem; cbeg[nchunks++] = at; at += t; }
-    cbeg[nchunks] = n;
-  }
+  int cbeg[HALF + 1];
+  const int nchunks = b2host::stage_schedule (n, ROWS_CHUNK, cbeg);
   static const bool trace = std::getenv ("B200TSDF_TRACE_ROWS") != nullptr;
   double t_wait = 0, t_pack = 0, t_enq = 0;
   auto now = [] { return std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now ().time_since_epoch ()).count (); };

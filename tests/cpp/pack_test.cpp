@@ -69,6 +69,18 @@ int main ()
       for (auto& h : hit) CHECK (h.load () == 1);
     }
   }
+  // stage schedule of b200tsdf_integrate_batch_rows: covers [0, n) with increasing boundaries, stages never longer than the chunk,
+  // the last stage at most 2 frames (when n > 2), never more than n stages
+  for (int chunk = 1; chunk <= 32; ++chunk)
+    for (int n = 1; n <= 32; ++n)
+    {
+      int cb[33];
+      const int k = b2host::stage_schedule (n, chunk, cb);
+      CHECK (k >= 1 && k <= n && cb[0] == 0 && cb[k] == n);
+      for (int c = 0; c < k; ++c) CHECK (cb[c + 1] > cb[c] && cb[c + 1] - cb[c] <= std::max (chunk, 1));
+      if (n > 2) CHECK (cb[k] - cb[k - 1] <= 2);
+    }
+  { int cb[33]; CHECK (b2host::stage_schedule (32, 8, cb) == 6 && cb[1] == 8 && cb[3] == 24 && cb[4] == 28 && cb[5] == 30); }
   if (fails) return 1;
   std::puts ("OK");
   return 0;
