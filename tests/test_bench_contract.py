@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -29,9 +31,11 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-def test_committed_gpu_bench_line_has_every_contract_key():
-    """profiles/r1_bench.json is the line `python bench.py` printed on the B200 box: check its shape against the contract."""
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench.json")))
+@pytest.mark.parametrize("name", ["r1_bench.json", "r2_bench.json"])
+def test_committed_gpu_bench_line_has_every_contract_key(name):
+    """profiles/rN_bench.json is the line `python bench.py` printed on the B200 box at the end of round N: check its shape against
+    the contract."""
+    d = json.load(open(os.path.join(ROOT, "profiles", name)))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -39,10 +43,22 @@ def test_committed_gpu_bench_line_has_every_contract_key():
     assert "workload" in d["config"] and "l2" in d["config"] and d["data"] == "synthetic" and d["dtype"] == "f32"
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     e = d["e2e"]
-    assert e["unit"] == "frames/s" and 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 32 * 640 * 480 * 32 and e["d2h_bytes_per_step"] > 0
+    # bytes that crossed PCIe per 32-frame step: the caller's 32-byte points (round 1), or the 16-byte pixels the host packed them to
+    packed = bool(e.get("host_pack", {}).get("enabled"))
+    assert e["unit"] == "frames/s" and 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 32 * 640 * 480 * (16 if packed else 32) and e["d2h_bytes_per_step"] > 0
+    if packed:
+        assert e["host_pack"]["input_bytes_per_step"] == 32 * 640 * 480 * 32 and e["host_pack"]["threads"] >= 1
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "frames/s" and c["sample"]
     assert d["gpu_launches"] == 4 * 32 * d["steps"]                      # four kernels per frame, 32 frames per step
     assert abs(d["value"] - 32 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    if name == "r2_bench.json":
+        # round 2: one graph launch per 32-frame step, a batched roofline figure next to the event-timed one, the loaded-host leg
+        assert d["graph_launches"] == d["steps"]
+        b = r["batched"]
+        assert b["frames_per_graph_launch"] == 32 and abs(b["frac"] - b["achieved"] / r["peak"]) < 1e-9 and b["frac"] >= r["frac"]
+        hl = d["host_load_leg"]
+        assert hl["unit"] == "frames/s" and len(hl["repeats"]) == 3 and abs(hl["value"] - sorted(hl["repeats"])[1]) < 1e-9
+        assert hl["value"] > 0.9 * d["value"]                            # the device-resident rate does not depend on an idle host
