@@ -7,14 +7,14 @@
 //   1. a top-down sweep over levels C .. B-1 (B = L-3, the block-root level): one thread per
 //      visited node decides "already split / split now by proximity / update as a leaf" and
 //      appends its children to the next level's queue (k_upper_down);
-//   2. one warp per visited block root: the whole 1+8+64+512-node subtree is staged in shared
-//      memory, swept top-down and bottom-up with warp ballots, and written back (k_blocks);
+//   2. one warp per visited block root sweeps the 1+8+64+512-node subtree top-down and bottom-up with warp
+//      ballots, updating the brick in place (k_bricks, brick_direct.cuh);
 //   3. a bottom-up sweep over levels B-1 .. C that folds the children's return codes, prunes
 //      all-empty children and applies the fall-through leaf update (k_upper_up).
 // Speculative splits are safe because storage of non-existent nodes is always fresh (see
 // tsdf_core.cuh).  The one case that is not separable — a node whose pre-existing children are
-// all pruned AND which then re-splits in the same call — is detected and
-// handed to the general depth-first routine update_voxel_dfs for that subtree only.
+// all pruned AND which then re-splits in the same call — is an ordinary leaf visit of the
+// flat layout once the prune has been written (leaf_visit_warp8 / update_voxel_dfs for that subtree only).
 #pragma once
 #include "tsdf_core.cuh"
 #include "obs_fast.cuh"
@@ -424,8 +424,8 @@ __device__ __forceinline__ void path_center (const float* c0, float off, int k, 
 // k_celltop_down: one CTA per culled coarse cell.  All 585 nodes of the cell's upper pyramid (cell + 8 + 64 + 512
 // block roots) are OBSERVED SPECULATIVELY in parallel (observation is a pure function of geometry and frame) while
 // the tier-1 brick is staged into shared memory, so the level-by-level decisions run from shared memory instead
-// of a chain of dependent DRAM loads.  Interior block roots are queued for k_blocks exactly as before.
-// k_celltop_up: one WARP per cell folds the return codes with ballots (the bottom-up half of k_blocks, operating on
+// of a chain of dependent DRAM loads.  Interior block roots are queued for k_bricks.
+// k_celltop_up: one WARP per cell folds the return codes with ballots (the bottom-up half of the block sweep, operating on
 // the brick in global memory: only pruned nodes are touched).
 constexpr int TOP_THREADS = 256;
 constexpr int TOP_NODES = 585;                       // flat index f: 0 = cell, 1..8, 9..72, 73..584
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__ (TOP_THREADS) k_celltop_down (Params p, const 
       }
       __syncthreads ();
     }
-    // ---- interior block roots -> block list (+ their QNode for k_blocks) ----
+    // ---- interior block roots -> block list (+ their QNode for k_bricks) ----
     constexpr int STRIDE = 585;
     for (int base = 0; base < 512; base += TOP_THREADS)
     {
