@@ -1176,7 +1176,14 @@ static int integrate_host (b200tsdf* h, const void* points, size_t stride, int x
     {
       cudaFree (h->d_frame[i]); h->d_frame[i] = nullptr; CK (cudaMalloc (&h->d_frame[i], cap));
       h->h_fpack[i].release ();
-      if (hpack && h->h_fpack[i].alloc (cap)) return h->fail (B200TSDF_ENOMEM, "pinned staging for the packed upload");
+      if (hpack && h->h_fpack[i].alloc (cap))
+      {
+        // no pinned staging to be had on this system: upload the points as they are from now on
+        h->host_pack = 0;
+        for (int k = 0; k < 2; ++k) h->h_fpack[k].release ();
+        h->frame_cap = 0;                                  // (d_frame[] is re-sized by the unpacked path)
+        return integrate_host (h, points, stride, xyz_off, rgba_off, width, height, pose, wait_copy);
+      }
     }
     h->frame_cap = cap;
     h->frame_no = 0;

@@ -184,7 +184,13 @@ int b200tsdf_integrate_batch_rows (b200tsdf_t* h, int n, const void* const* rows
       h->rows_raw_cap = h->rows_full_cap = h->pack_cap = 0;
       if (need_raw) CK (cudaMalloc (&h->d_rows_raw[k], need_raw));
       CK (cudaMalloc (&h->d_rows_full[k], need_full));
-      if (need_pack && h->h_pack[k].alloc (need_pack)) return h->fail (B200TSDF_ENOMEM, "pinned staging for the packed upload");
+      if (need_pack && h->h_pack[k].alloc (need_pack))
+      {
+        // no pinned staging to be had on this system: upload the points as they are from now on (the caps are 0: everything is re-sized)
+        h->host_pack = 0;
+        for (int j = 0; j < 2; ++j) h->h_pack[j].release ();
+        return b200tsdf_integrate_batch_rows (h, n, rows, stride, xyz_off, rgba_off, width, height, poses_c2w);
+      }
       h->rows_used[k] = false;
     }
     h->rows_raw_cap = need_raw; h->rows_full_cap = need_full; h->pack_cap = need_pack;
