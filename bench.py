@@ -6,8 +6,10 @@ frames (ICL-NUIM-shaped interior stream S2, colour on, 2048^3 / 10 m grid: BASEL
 configs[2]).  The JSON line carries
   value        frames/s with the clouds already resident in HBM (b200tsdf_integrate_batch_device: one
                CUDA-graph launch per step of 32 frames),
-  e2e          frames/s through the public API from pinned HOST buffers (H2D inside the timed
-               region, a D2H read of the per-step result),
+  e2e          frames/s through the public API (b200tsdf_integrate_batch_rows) from pinned HOST buffers: host packing
+               to 16-byte pixels (one rank) or raw row slices + NVLink all-gather (more ranks), H2D and a D2H read of
+               the per-step result inside the timed region,
+  host_load_leg the device-resident leg again with every host core busy (median of three repeats),
   roofline     achieved algorithmic GB/s of the dominant kernel against the measured HBM peak,
   cpu_baseline the reference's CPU path timed on this box's host cores (bounded sample).
 `--impl reference` times the CPU arm alone (oracle/_ref = the reference's own sources when they
